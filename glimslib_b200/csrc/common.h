@@ -1,0 +1,177 @@
+// Internal declarations shared by the translation units of libglims_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/glims_b200.h"
+
+typedef long long i64;
+
+#define GL_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            char b_[512];                                                               \
+            snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call,          \
+                     cudaGetErrorString(e_));                                           \
+            throw GlError(GLIMS_ERR_CUDA, b_);                                          \
+        }                                                                               \
+    } while (0)
+
+struct GlError {
+    int code;
+    std::string msg;
+    GlError(int c, const std::string& m) : code(c), msg(m) {}
+};
+
+constexpr int SLICE = 32;          // SELL-32: one warp lane per block row
+constexpr int MAX_MAT = 64;        // material table rows staged in shared memory
+constexpr int MAT_STRIDE = 6;      // mu, lambda, D, rho, gamma, beta=(2mu+d*lambda)*gamma
+
+// Sliced-ELL block pattern of one vertex graph. Slot s of row r (block j of the row):
+//   s = slice_off[r/32] + j*32 + r%32 ; value k of an ncomp-block: (s & ~31)*ncomp + k*32 + (s & 31).
+// Padding slots carry col = own row and zero values.
+struct SellPattern {
+    int n_rows = 0;
+    int n_slices = 0;
+    i64 n_slots = 0;       // padded
+    i64 nnzb = 0;          // true blocks
+    i64* slice_off = nullptr;   // [n_slices+1]
+    int* slice_w = nullptr;     // [n_slices]
+    int* col = nullptr;         // [n_slots]
+    i64* rowptr = nullptr;      // [n_rows+1] CSR (true entries, columns ascending)
+    int* diag = nullptr;        // [n_rows] slot of the diagonal block
+    int max_w = 0;
+};
+
+__host__ __device__ inline i64 vidx(i64 s, int k, int ncomp) {
+    return (s & ~(i64)31) * ncomp + (i64)k * 32 + (s & 31);
+}
+
+struct AmgLevel;   // amg.cu
+struct Amg;
+
+struct Halo {       // multi-GPU ghost exchange plan (device copies)
+    bool active = false;
+    int n_ranks = 1, rank = 0;
+    void* comm = nullptr;          // ncclComm_t
+    i64 n_owned = 0;
+    std::vector<int> peers;
+    std::vector<i64> send_ptr, recv_ptr;
+    int* send_idx = nullptr;       // device
+    double* send_buf = nullptr;    // device, send_ptr.back() * nb doubles (max)
+    i64 n_send = 0;
+};
+
+struct glims_ctx {
+    int dim = 0, nb = 0, device = 0;
+    i64 n_v = 0, n_c = 0, ndof = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    i64 launches = 0;
+
+    // mesh
+    double* coords = nullptr;   // [n_v][dim]
+    int* cells = nullptr;       // [n_c][nb]
+    int* cell_mat = nullptr;    // [n_c]
+    int n_mat = 0;
+    double* mat = nullptr;      // [n_mat][MAT_STRIDE] device
+    double dt = 1.0;
+    bool have_mat = false, kconst_valid = false;
+
+    // pattern + scatter maps
+    SellPattern pat;
+    int* eslot = nullptr;       // [n_c][nb*nb] slot per (a,b) pair: element -> matrix scatter map
+    // transposed map for the gather kernel: contributors of every slot, CSR over slots
+    i64* gptr = nullptr;        // [n_slots+1]
+    int* gent = nullptr;        // [n_c*nb*nb] packed: element<<4 | a<<2 | b
+    bool have_gather = false;
+
+    // matrices (SELL value layout, see vidx)
+    double *Kuu = nullptr, *Kuc = nullptr, *Kcc = nullptr;
+    // preconditioner data
+    double* dinv_uu = nullptr;  // [n_v][dim*dim] inverse diagonal blocks of K_uu
+    double* dinv_cc = nullptr;  // [n_v]
+    double* dinv_mono = nullptr;// [n_v][nb*nb]
+
+    // vectors, vertex-blocked [n_v][nb]
+    double *x = nullptr, *xprev = nullptr, *F = nullptr, *fext = nullptr, *dx = nullptr;
+    bool have_load = false;
+    // Dirichlet
+    i64 n_bc = 0;
+    i64* bc_dofs = nullptr;
+    double* bc_vals = nullptr;
+    i64 n_bc_u = 0, n_bc_c = 0;
+    unsigned char* bcmask = nullptr;   // [n_v] bit k set: dof (v,k) constrained
+
+    // Krylov workspace (allocated lazily)
+    double* work = nullptr;
+    i64 work_size = 0;
+    double* scal = nullptr;         // device scalars
+    double* partials = nullptr;     // block partial sums
+    unsigned* tickets = nullptr;
+    double* h_scal = nullptr;       // pinned host mirror
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+
+    Amg* amg = nullptr;
+    Halo halo;
+    bool first_step_done = false;
+};
+
+// ---------------- pattern.cu
+void build_pattern(glims_ctx* c);
+void build_gather_map(glims_ctx* c);
+
+// ---------------- kernels.cu (launch wrappers; all on c->stream)
+void launch_assemble(glims_ctx* c, int what, int variant);
+void launch_bc_values(glims_ctx* c, double* x);
+void launch_bc_residual(glims_ctx* c, double* F, const double* x);
+void launch_bc_matrix(glims_ctx* c, int what, bool sym);
+void launch_diag_inverse(glims_ctx* c, int which);   // 0 mono, 1 uu, 2 cc
+void launch_export_values(glims_ctx* c, double* Kuu, double* Kuc, double* Kcc);  // device CSR-order outputs
+
+struct SpmvDot {            // optional fused dot: out = sum_r y[r] . w[r]
+    const double* w = nullptr;
+    int slot = -1;          // scalar slot index in c->scal
+};
+// y = A x for block sizes: which 0 mono (nb x nb over K_uu,K_uc,K_cc), 1 K_uu (dim x dim), 2 K_cc (1x1)
+void launch_spmv(glims_ctx* c, int which, const double* x, double* y, SpmvDot dot = SpmvDot());
+// y_u[n_v][dim] = K_uc x_c
+void launch_spmv_uc(glims_ctx* c, const double* xc, double* yu);
+
+// generic SELL block SpMV used by AMG levels: y = A x, A blocks BRxBC stored [slot][BR*BC]
+void launch_spmv_generic(glims_ctx* c, const SellPattern& p, const double* A, int bs, const double* x, double* y);
+
+// vector kernels with device-resident scalars; scal indices refer to c->scal
+enum { S_RZ = 0, S_PAP, S_RR, S_RZNEW, S_BN, S_TMP0, S_TMP1, S_TMP2, S_TMP3, S_GM0 /* 64 slots from here */, S_COUNT = 128 };
+void launch_dot(glims_ctx* c, const double* a, const double* b, i64 n, int slot);
+void launch_multi_dot(glims_ctx* c, const double* V, i64 ld, int k, const double* w, i64 n, int slot0);
+void launch_axpy(glims_ctx* c, double alpha, const double* x, double* y, i64 n);               // y += alpha x
+void launch_scale(glims_ctx* c, double alpha, double* x, i64 n);
+void launch_copy(glims_ctx* c, const double* x, double* y, i64 n);
+void launch_zero(glims_ctx* c, double* x, i64 n);
+// CG fused updates (alpha = scal[num]/scal[den] computed on device)
+void launch_cg_update_xr(glims_ctx* c, double* x, double* r, const double* p, const double* Ap, i64 n,
+                         int s_num, int s_den, int s_rr);
+void launch_cg_update_p(glims_ctx* c, double* p, const double* z, i64 n, int s_num, int s_den);
+// z = Dinv r (block size bs), fused dot(r,z) -> slot
+void launch_block_jacobi(glims_ctx* c, const double* dinv, int bs, const double* r, double* z, i64 n_rows, int s_rz);
+// blocked <-> split
+void launch_extract(glims_ctx* c, const double* xb, double* xu, double* xc);   // either may be null
+void launch_insert_add(glims_ctx* c, double* xb, const double* du, const double* dc, double alpha);
+void launch_split_norms(glims_ctx* c, const double* F, int s0);   // |F_u|^2, |F_c|^2 -> slots s0, s0+1
+void launch_multi_axpy(glims_ctx* c, const double* V, i64 ld, int k, const double* coef_dev, double sign, double* w, i64 n);
+void read_scalars(glims_ctx* c, int slot0, int n, double* out);   // sync
+void flush_l2(glims_ctx* c);
+
+// ---------------- amg.cu
+void amg_setup(glims_ctx* c);
+void amg_free(glims_ctx* c);
+void amg_vcycle(glims_ctx* c, const double* r, double* z);   // z = M^-1 r on K_uu ([n_v][dim] vectors)
+
+// ---------------- comm.cu
+void halo_exchange(glims_ctx* c, double* xb, int bs);        // fill ghost values of a blocked vector
+void allreduce_scalars(glims_ctx* c, int slot0, int n);      // in-place sum over ranks of c->scal slots

@@ -1,0 +1,880 @@
+// Device kernels of the hot path: element residual/Jacobian (K1/K2), Dirichlet elimination (K3),
+// SELL-32 block SpMV (K4), block-Jacobi (K5), fused Krylov vector updates with deterministic
+// shuffle reductions (K6).  sm_100a; FP64 throughout; no tensor cores (nothing here is a dense
+// contraction) -- every kernel is bound by HBM traffic or FP64 issue.
+#include "common.h"
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblk(i64 n, int t = TPB) { return (int)((n + t - 1) / t); }
+inline int red_grid(glims_ctx* c, i64 n) {   // grid for grid-stride reduction kernels
+    i64 need = (n + TPB - 1) / TPB;
+    i64 cap = 148 * 8;
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+constexpr int MAXBLK = 148 * 8;
+
+// ------------------------------------------------------------------------------------------------
+// deterministic grid reduction: per-block shuffle reduce -> partials[blk]; the last block to arrive
+// sums the partials in a fixed order and publishes the scalar.
+template <int NV>
+__device__ inline void grid_reduce(double (&v)[NV], double* partials, unsigned* tickets, double* scal, int slot0) {
+    __shared__ double sm[NV][TPB / 32];
+    __shared__ bool last;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[k][wid] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < TPB / 32; ++w) s += sm[threadIdx.x][w];
+        partials[(i64)(slot0 + threadIdx.x) * MAXBLK + blockIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicInc(&tickets[slot0], gridDim.x - 1);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        for (int k = 0; k < NV; ++k) {
+            double s = 0;
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += TPB)
+                s += __ldcg(&partials[(i64)(slot0 + k) * MAXBLK + b]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            __syncthreads();
+            if (lane == 0) sm[0][wid] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0;
+                for (int w = 0; w < TPB / 32; ++w) t += sm[0][w];
+                scal[slot0 + k] = t;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// element geometry: barycentric gradients and volume of a P1 simplex
+template <int D> struct Geo { double g[D + 1][D]; double vol; };
+
+__device__ inline void geometry(const double (&X)[3][2], Geo<2>& G) {
+    double j00 = X[1][0] - X[0][0], j01 = X[2][0] - X[0][0];
+    double j10 = X[1][1] - X[0][1], j11 = X[2][1] - X[0][1];
+    double det = j00 * j11 - j01 * j10, id = 1.0 / det;
+    G.g[1][0] = j11 * id;  G.g[1][1] = -j01 * id;
+    G.g[2][0] = -j10 * id; G.g[2][1] = j00 * id;
+    G.g[0][0] = -(G.g[1][0] + G.g[2][0]);
+    G.g[0][1] = -(G.g[1][1] + G.g[2][1]);
+    G.vol = 0.5 * fabs(det);
+}
+__device__ inline void geometry(const double (&X)[4][3], Geo<3>& G) {
+    double e1[3], e2[3], e3[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { e1[k] = X[1][k] - X[0][k]; e2[k] = X[2][k] - X[0][k]; e3[k] = X[3][k] - X[0][k]; }
+    double c1[3] = {e2[1] * e3[2] - e2[2] * e3[1], e2[2] * e3[0] - e2[0] * e3[2], e2[0] * e3[1] - e2[1] * e3[0]};
+    double c2[3] = {e3[1] * e1[2] - e3[2] * e1[1], e3[2] * e1[0] - e3[0] * e1[2], e3[0] * e1[1] - e3[1] * e1[0]};
+    double c3[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    double det = e1[0] * c1[0] + e1[1] * c1[1] + e1[2] * c1[2], id = 1.0 / det;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        G.g[1][k] = c1[k] * id; G.g[2][k] = c2[k] * id; G.g[3][k] = c3[k] * id;
+        G.g[0][k] = -(G.g[1][k] + G.g[2][k] + G.g[3][k]);
+    }
+    G.vol = fabs(det) * (1.0 / 6.0);
+}
+
+template <int D> struct Consts;
+template <> struct Consts<2> { static constexpr double mass = 1.0 / 12.0; static constexpr double kappa = 1.0 / 60.0; };
+template <> struct Consts<3> { static constexpr double mass = 1.0 / 20.0; static constexpr double kappa = 1.0 / 120.0; };
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2, element-parallel variant: one thread per element, scatter through the precomputed
+// element->slot map with RED.ADD.F64.  RES: residual; KCONST: K_uu, K_uc; KCC: K_cc.
+template <int D, bool RES, bool KCONST, bool KCC>
+__global__ void __launch_bounds__(128)
+k_assemble_atomic(const double* __restrict__ coords, const int* __restrict__ cells, const int* __restrict__ cell_mat,
+                  const double* __restrict__ mat_g, int n_mat, i64 n_c, i64 n_own, double dt,
+                  const double* __restrict__ x, const double* __restrict__ xprev, const int* __restrict__ eslot,
+                  double* __restrict__ F, double* __restrict__ Kuu, double* __restrict__ Kuc, double* __restrict__ Kcc) {
+    constexpr int NB = D + 1;
+    __shared__ double smat[MAX_MAT * MAT_STRIDE];
+    for (int t = threadIdx.x; t < n_mat * MAT_STRIDE; t += blockDim.x) smat[t] = mat_g[t];
+    __syncthreads();
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= n_c) return;
+    int v[NB];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) v[a] = cells[e * NB + a];
+    double X[NB][D];
+#pragma unroll
+    for (int a = 0; a < NB; ++a)
+#pragma unroll
+        for (int k = 0; k < D; ++k) X[a][k] = coords[(i64)v[a] * D + k];
+    Geo<D> G;
+    geometry(X, G);
+    const double* m = &smat[cell_mat[e] * MAT_STRIDE];
+    const double mu = m[0], lam = m[1], Dc = m[2], rho = m[3], beta = m[5];
+    const double vol = G.vol;
+    double cv[NB], S = 0, Q = 0;
+#pragma unroll
+    for (int a = 0; a < NB; ++a) { cv[a] = x[(i64)v[a] * NB + D]; S += cv[a]; Q += cv[a] * cv[a]; }
+
+    if (RES) {
+        double u[NB][D], cp[NB], Sp = 0;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) u[a][k] = x[(i64)v[a] * NB + k];
+            cp[a] = xprev[(i64)v[a] * NB + D];
+            Sp += cp[a];
+        }
+        double gu[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                double s = 0;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) s += u[b][i] * G.g[b][j];
+                gu[i][j] = s;
+            }
+        double tr = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) tr += gu[i][i];
+        double sig[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) sig[i][j] = mu * (gu[i][j] + gu[j][i]) + (i == j ? lam * tr : 0.0);
+        const double cbar = S / NB;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) {
+            if (v[a] >= n_own) continue;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double s = 0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) s += sig[i][j] * G.g[a][j];
+                atomicAdd(&F[(i64)v[a] * NB + i], vol * (s - beta * cbar * G.g[a][i]));
+            }
+            double diff = 0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                double gg = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) gg += G.g[a][k] * G.g[b][k];
+                diff += gg * cv[b];
+            }
+            double massc = Consts<D>::mass * (cv[a] + S), massp = Consts<D>::mass * (cp[a] + Sp);
+            double trip = Consts<D>::kappa * (2.0 * cv[a] * cv[a] + 2.0 * cv[a] * S + S * S + Q);
+            atomicAdd(&F[(i64)v[a] * NB + D], vol * (massc - massp + dt * Dc * diff - dt * rho * (massc - trip)));
+        }
+    }
+    if (KCONST || KCC) {
+#pragma unroll
+        for (int a = 0; a < NB; ++a) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const int s = eslot[e * (NB * NB) + a * NB + b];
+                if (s < 0) continue;
+                double gg = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) gg += G.g[a][k] * G.g[b][k];
+                if (KCONST) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j) {
+                            double val = vol * (mu * ((i == j ? gg : 0.0) + G.g[a][j] * G.g[b][i]) + lam * G.g[a][i] * G.g[b][j]);
+                            atomicAdd(&Kuu[vidx(s, i * D + j, D * D)], val);
+                        }
+                        atomicAdd(&Kuc[vidx(s, i, D)], -beta * vol * (1.0 / NB) * G.g[a][i]);
+                    }
+                }
+                if (KCC) {
+                    double ml = Consts<D>::mass * (a == b ? 2.0 : 1.0);
+                    double tl = 2.0 * Consts<D>::kappa * (a == b ? 4.0 * cv[a] + 2.0 * S : cv[a] + cv[b] + S);
+                    atomicAdd(&Kcc[s], vol * (ml * (1.0 - dt * rho) + dt * Dc * gg + dt * rho * tl));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, row-parallel gather variant: one thread per matrix slot walks the transposed scatter map
+// (the (element, a, b) triples that contribute to the slot), recomputes each element's gradients
+// from L2-resident coordinates and writes every matrix value exactly once -- no atomics, no
+// pre-zeroing, deterministic summation order.
+template <int D, bool KCONST, bool KCC>
+__global__ void __launch_bounds__(128)
+k_assemble_gather(const double* __restrict__ coords, const int* __restrict__ cells, const int* __restrict__ cell_mat,
+                  const double* __restrict__ mat_g, int n_mat, double dt, const double* __restrict__ x,
+                  const i64* __restrict__ gptr, const int* __restrict__ gent, i64 n_slots,
+                  double* __restrict__ Kuu, double* __restrict__ Kuc, double* __restrict__ Kcc) {
+    constexpr int NB = D + 1;
+    __shared__ double smat[MAX_MAT * MAT_STRIDE];
+    for (int t = threadIdx.x; t < n_mat * MAT_STRIDE; t += blockDim.x) smat[t] = mat_g[t];
+    __syncthreads();
+    i64 s = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    double auu[D * D], auc[D], acc = 0;
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) auu[k] = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) auc[k] = 0;
+    const i64 t0 = gptr[s], t1 = gptr[s + 1];
+    for (i64 t = t0; t < t1; ++t) {
+        const int ent = gent[t];
+        const i64 e = ent >> 4;
+        const int a = (ent >> 2) & 3, b = ent & 3;
+        int v[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) v[q] = cells[e * NB + q];
+        double X[NB][D];
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+            for (int k = 0; k < D; ++k) X[q][k] = coords[(i64)v[q] * D + k];
+        Geo<D> G;
+        geometry(X, G);
+        const double* m = &smat[cell_mat[e] * MAT_STRIDE];
+        const double mu = m[0], lam = m[1], Dc = m[2], rho = m[3], beta = m[5];
+        double ga[D], gb[D], gg = 0;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {   // select without dynamic register indexing
+            if (q == a) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) ga[k] = G.g[q][k];
+            }
+            if (q == b) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) gb[k] = G.g[q][k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) gg += ga[k] * gb[k];
+        if (KCONST) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    auu[i * D + j] += G.vol * (mu * ((i == j ? gg : 0.0) + ga[j] * gb[i]) + lam * ga[i] * gb[j]);
+                auc[i] += -beta * G.vol * (1.0 / NB) * ga[i];
+            }
+        }
+        if (KCC) {
+            double S = 0, ca = 0, cb = 0;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                double cq = x[(i64)v[q] * NB + D];
+                S += cq;
+                if (q == a) ca = cq;
+                if (q == b) cb = cq;
+            }
+            double ml = Consts<D>::mass * (a == b ? 2.0 : 1.0);
+            double tl = 2.0 * Consts<D>::kappa * (a == b ? 4.0 * ca + 2.0 * S : ca + cb + S);
+            acc += G.vol * (ml * (1.0 - dt * rho) + dt * Dc * gg + dt * rho * tl);
+        }
+    }
+    if (KCONST) {
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) Kuu[vidx(s, k, D * D)] = auu[k];
+#pragma unroll
+        for (int k = 0; k < D; ++k) Kuc[vidx(s, k, D)] = auc[k];
+    }
+    if (KCC) Kcc[s] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 Dirichlet
+__global__ void k_bc_values(const i64* __restrict__ dofs, const double* __restrict__ vals, i64 n, double* x) {
+    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (t < n) x[dofs[t]] = vals[t];
+}
+__global__ void k_bc_residual(const i64* __restrict__ dofs, const double* __restrict__ vals, i64 n,
+                              const double* __restrict__ x, double* F) {
+    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (t < n) F[dofs[t]] = x[dofs[t]] - vals[t];
+}
+// one block per slice: zero Dirichlet rows (and, if sym, columns) of the requested matrices.
+// bcmask[v] has bit k set when dof (v,k) is constrained.
+template <int D>
+__global__ void k_bc_matrix(const unsigned char* __restrict__ bcmask, const i64* __restrict__ slice_off,
+                            const int* __restrict__ slice_w, const int* __restrict__ col, int n_rows, int what, bool sym,
+                            double* Kuu, double* Kuc, double* Kcc) {
+    const int S = blockIdx.x;
+    const i64 base = slice_off[S];
+    const int w = slice_w[S];
+    for (int t = threadIdx.x; t < w * 32; t += blockDim.x) {
+        const int r = S * 32 + (t & 31);
+        if (r >= n_rows) continue;
+        const i64 s = base + t;
+        const unsigned mr = bcmask[r];
+        const unsigned mc = sym ? bcmask[col[s]] : 0u;
+        if ((mr | mc) == 0u) continue;
+        if (what & GLIMS_ASM_KCONST) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (((mr >> i) | (mc >> j)) & 1u) Kuu[vidx(s, i * D + j, D * D)] = 0.0;
+                if (((mr >> i) | (mc >> D)) & 1u) Kuc[vidx(s, i, D)] = 0.0;
+            }
+        }
+        if ((what & GLIMS_ASM_KCC) && (((mr | mc) >> D) & 1u)) Kcc[s] = 0.0;
+    }
+}
+template <int D>
+__global__ void k_bc_diag(const i64* __restrict__ dofs, i64 n, i64 n_own, const int* __restrict__ diag, int what,
+                          double* Kuu, double* Kcc) {
+    constexpr int NB = D + 1;
+    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    i64 dof = dofs[t];
+    int v = (int)(dof / NB), k = (int)(dof - (i64)v * NB);
+    if (v >= n_own) return;
+    i64 s = diag[v];
+    if (k < D) { if (what & GLIMS_ASM_KCONST) Kuu[vidx(s, k * D + k, D * D)] = 1.0; }
+    else if (what & GLIMS_ASM_KCC) Kcc[s] = 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 SpMV, SELL-32: one thread per block row, slice width uniform per warp, value loads coalesced
+// (component-major inside each 32-slot group), x gathered through L1/L2.
+template <int BR, int BC, bool DOT>
+__global__ void __launch_bounds__(TPB)
+k_spmv_block(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+             const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, int n_rows,
+             const double* __restrict__ wdot, double* partials, unsigned* tickets, double* scal, int slot) {
+    double local[1] = {0.0};
+    const int n_tiles = (n_rows + TPB - 1) / TPB;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int r = tile * TPB + threadIdx.x;
+        const int S = r >> 5, lane = r & 31;
+        double acc[BR];
+#pragma unroll
+        for (int i = 0; i < BR; ++i) acc[i] = 0.0;
+        if (S * 32 < n_rows) {
+            const i64 base = slice_off[S];
+            const int w = slice_w[S];
+            for (int j = 0; j < w; ++j) {
+                const i64 g = base + (i64)j * 32;
+                const int cidx = __ldg(&col[g + lane]);
+                double xv[BC];
+#pragma unroll
+                for (int b = 0; b < BC; ++b) xv[b] = __ldg(&x[(i64)cidx * BC + b]);
+                const double* Ag = A + g * (BR * BC) + lane;
+#pragma unroll
+                for (int i = 0; i < BR; ++i)
+#pragma unroll
+                    for (int b = 0; b < BC; ++b) acc[i] += __ldcs(&Ag[(i * BC + b) * 32]) * xv[b];
+            }
+        }
+        if (r < n_rows) {
+#pragma unroll
+            for (int i = 0; i < BR; ++i) y[(i64)r * BR + i] = acc[i];
+            if (DOT) {
+#pragma unroll
+                for (int i = 0; i < BR; ++i) local[0] += acc[i] * wdot[(i64)r * BR + i];
+            }
+        }
+    }
+    if (DOT) grid_reduce<1>(local, partials, tickets, scal, slot);
+}
+
+// monolithic Jacobian J = [[K_uu, K_uc], [0, K_cc]] on vertex-blocked vectors [n_v][D+1]
+template <int D, bool DOT>
+__global__ void __launch_bounds__(TPB)
+k_spmv_mono(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+            const double* __restrict__ Kuu, const double* __restrict__ Kuc, const double* __restrict__ Kcc,
+            const double* __restrict__ x, double* __restrict__ y, int n_rows, const double* __restrict__ wdot,
+            double* partials, unsigned* tickets, double* scal, int slot) {
+    constexpr int NB = D + 1;
+    double local[1] = {0.0};
+    const int n_tiles = (n_rows + TPB - 1) / TPB;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int r = tile * TPB + threadIdx.x;
+        const int S = r >> 5, lane = r & 31;
+        double acc[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) acc[i] = 0.0;
+        if (S * 32 < n_rows) {
+            const i64 base = slice_off[S];
+            const int w = slice_w[S];
+            for (int j = 0; j < w; ++j) {
+                const i64 g = base + (i64)j * 32;
+                const int cidx = __ldg(&col[g + lane]);
+                double xv[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) xv[b] = __ldg(&x[(i64)cidx * NB + b]);
+                const double* Au = Kuu + g * (D * D) + lane;
+                const double* Ac = Kuc + g * D + lane;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+#pragma unroll
+                    for (int b = 0; b < D; ++b) acc[i] += __ldcs(&Au[(i * D + b) * 32]) * xv[b];
+                    acc[i] += __ldcs(&Ac[i * 32]) * xv[D];
+                }
+                acc[D] += __ldcs(&Kcc[g + lane]) * xv[D];
+            }
+        }
+        if (r < n_rows) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) y[(i64)r * NB + i] = acc[i];
+            if (DOT) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i) local[0] += acc[i] * wdot[(i64)r * NB + i];
+            }
+        }
+    }
+    if (DOT) grid_reduce<1>(local, partials, tickets, scal, slot);
+}
+
+// y_u = K_uc x_c  (D x 1 blocks)
+template <int D>
+__global__ void __launch_bounds__(TPB)
+k_spmv_uc(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+          const double* __restrict__ Kuc, const double* __restrict__ xc, double* __restrict__ yu, int n_rows) {
+    const int r = blockIdx.x * TPB + threadIdx.x;
+    const int S = r >> 5, lane = r & 31;
+    if (S * 32 >= n_rows) return;
+    double acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.0;
+    const i64 base = slice_off[S];
+    const int w = slice_w[S];
+    for (int j = 0; j < w; ++j) {
+        const i64 g = base + (i64)j * 32;
+        const double xv = __ldg(&xc[col[g + lane]]);
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc[i] += Kuc[g * D + i * 32 + lane] * xv;
+    }
+    if (r < n_rows)
+#pragma unroll
+        for (int i = 0; i < D; ++i) yu[(i64)r * D + i] = acc[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagonal-block inverses (K5 block-Jacobi data)
+template <int N>
+__device__ inline void invert_small(double (&a)[N][N]) {   // Gauss-Jordan without pivoting (SPD / diagonally safe blocks)
+    double inv[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) inv[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+        double ip = 1.0 / a[p][p];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { a[p][j] *= ip; inv[p][j] *= ip; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i == p) continue;
+            double f = a[i][p];
+#pragma unroll
+            for (int j = 0; j < N; ++j) { a[i][j] -= f * a[p][j]; inv[i][j] -= f * inv[p][j]; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[i][j] = inv[i][j];
+}
+
+template <int D>
+__global__ void k_diag_inverse(const int* __restrict__ diag, int n_rows, int which, const double* __restrict__ Kuu,
+                               const double* __restrict__ Kuc, const double* __restrict__ Kcc, double* out) {
+    constexpr int NB = D + 1;
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    i64 s = diag[r];
+    if (which == 2) { out[r] = 1.0 / Kcc[s]; return; }
+    if (which == 1) {
+        double a[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) a[i][j] = Kuu[vidx(s, i * D + j, D * D)];
+        invert_small<D>(a);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) out[(i64)r * D * D + i * D + j] = a[i][j];
+        return;
+    }
+    double a[NB][NB];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) a[i][j] = Kuu[vidx(s, i * D + j, D * D)];
+        a[i][D] = Kuc[vidx(s, i, D)];
+        a[D][i] = 0.0;
+    }
+    a[D][D] = Kcc[s];
+    invert_small<NB>(a);
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) out[(i64)r * NB * NB + i * NB + j] = a[i][j];
+}
+
+template <int BS>
+__global__ void __launch_bounds__(TPB)
+k_block_jacobi(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ z, i64 n_rows,
+               double* partials, unsigned* tickets, double* scal, int slot) {
+    double local[1] = {0.0};
+    for (i64 row = blockIdx.x * (i64)TPB + threadIdx.x; row < n_rows; row += (i64)gridDim.x * TPB) {
+        double rv[BS], zv[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) rv[i] = r[row * BS + i];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            double s = 0;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) s += dinv[row * BS * BS + i * BS + j] * rv[j];
+            zv[i] = s;
+            z[row * BS + i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i) local[0] += rv[i] * zv[i];
+    }
+    if (slot >= 0) grid_reduce<1>(local, partials, tickets, scal, slot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6 vector kernels
+__global__ void __launch_bounds__(TPB)
+k_dot(const double* __restrict__ a, const double* __restrict__ b, i64 n, double* partials, unsigned* tickets,
+      double* scal, int slot) {
+    double local[1] = {0.0};
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) local[0] += a[i] * b[i];
+    grid_reduce<1>(local, partials, tickets, scal, slot);
+}
+// h[i] = V_i . w for i < k (k <= 32), one pass over w
+__global__ void __launch_bounds__(TPB)
+k_multi_dot(const double* __restrict__ V, i64 ld, int k, const double* __restrict__ w, i64 n, double* partials,
+            unsigned* tickets, double* scal, int slot0) {
+    for (int i0 = 0; i0 < k; i0 += 4) {
+        double local[4] = {0, 0, 0, 0};
+        for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) {
+            double wi = w[i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i0 + q < k) local[q] += V[(i64)(i0 + q) * ld + i] * wi;
+        }
+        grid_reduce<4>(local, partials, tickets, scal, slot0 + i0);
+        __syncthreads();
+    }
+}
+__global__ void k_multi_axpy(const double* __restrict__ V, i64 ld, int k, const double* __restrict__ coef, double sign,
+                             double* __restrict__ w, i64 n) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) {
+        double s = w[i];
+        for (int q = 0; q < k; ++q) s += sign * coef[q] * V[(i64)q * ld + i];
+        w[i] = s;
+    }
+}
+__global__ void k_axpy(double alpha, const double* __restrict__ x, double* __restrict__ y, i64 n) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) y[i] += alpha * x[i];
+}
+__global__ void k_scale(double alpha, double* __restrict__ x, i64 n) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) x[i] *= alpha;
+}
+// x += a p ; r -= a Ap ; rr = r.r   with a = scal[num]/scal[den]
+__global__ void __launch_bounds__(TPB)
+k_cg_update_xr(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+               const double* __restrict__ Ap, i64 n, int s_num, int s_den, int s_rr, double* partials,
+               unsigned* tickets, double* scal) {
+    const double den = scal[s_den];
+    const double a = den != 0.0 ? scal[s_num] / den : 0.0;
+    double local[1] = {0.0};
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) {
+        x[i] += a * p[i];
+        double ri = r[i] - a * Ap[i];
+        r[i] = ri;
+        local[0] += ri * ri;
+    }
+    grid_reduce<1>(local, partials, tickets, scal, s_rr);
+}
+// p = z + (scal[num]/scal[den]) p
+__global__ void k_cg_update_p(double* __restrict__ p, const double* __restrict__ z, i64 n, int s_num, int s_den,
+                              const double* __restrict__ scal) {
+    const double den = scal[s_den];
+    const double b = den != 0.0 ? scal[s_num] / den : 0.0;
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) p[i] = z[i] + b * p[i];
+}
+template <int D>
+__global__ void k_extract(const double* __restrict__ xb, double* xu, double* xc, i64 n_v) {
+    constexpr int NB = D + 1;
+    for (i64 v = blockIdx.x * (i64)TPB + threadIdx.x; v < n_v; v += (i64)gridDim.x * TPB) {
+        if (xu)
+#pragma unroll
+            for (int k = 0; k < D; ++k) xu[v * D + k] = xb[v * NB + k];
+        if (xc) xc[v] = xb[v * NB + D];
+    }
+}
+template <int D>
+__global__ void k_insert_add(double* xb, const double* du, const double* dc, double alpha, i64 n_v) {
+    constexpr int NB = D + 1;
+    for (i64 v = blockIdx.x * (i64)TPB + threadIdx.x; v < n_v; v += (i64)gridDim.x * TPB) {
+        if (du)
+#pragma unroll
+            for (int k = 0; k < D; ++k) xb[v * NB + k] += alpha * du[v * D + k];
+        if (dc) xb[v * NB + D] += alpha * dc[v];
+    }
+}
+// |F_u|^2 and |F_c|^2 of a blocked vector -> slots s0, s0+1
+template <int D>
+__global__ void __launch_bounds__(TPB)
+k_split_norms(const double* __restrict__ F, i64 n_v, double* partials, unsigned* tickets, double* scal, int s0) {
+    constexpr int NB = D + 1;
+    double local[2] = {0.0, 0.0};
+    for (i64 v = blockIdx.x * (i64)TPB + threadIdx.x; v < n_v; v += (i64)gridDim.x * TPB) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) local[0] += F[v * NB + k] * F[v * NB + k];
+        local[1] += F[v * NB + D] * F[v * NB + D];
+    }
+    grid_reduce<2>(local, partials, tickets, scal, s0);
+}
+// F -= f_ext
+__global__ void k_sub(double* __restrict__ F, const double* __restrict__ f, i64 n) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) F[i] -= f[i];
+}
+// SELL -> CSR order gather of values for export
+template <int NC>
+__global__ void k_export(const i64* __restrict__ rowptr, const i64* __restrict__ slice_off, int n_rows,
+                         const double* __restrict__ A, double* out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    i64 base = slice_off[r >> 5];
+    for (i64 t = rowptr[r]; t < rowptr[r + 1]; ++t) {
+        i64 s = base + (t - rowptr[r]) * 32 + (r & 31);
+        for (int k = 0; k < NC; ++k) out[t * NC + k] = A[vidx(s, k, NC)];
+    }
+}
+__global__ void k_flush(double* buf, i64 n) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) buf[i] = (double)i;
+}
+
+}  // namespace
+
+// ================================================================================================
+// launch wrappers
+#define LAUNCHED(c) ((c)->launches++)
+
+template <int D>
+static void assemble_dim(glims_ctx* c, int what, int variant) {
+    constexpr int NB = D + 1;
+    i64 n_own = c->pat.n_rows;
+    const bool res = what & GLIMS_ASM_RESIDUAL, kconst = what & GLIMS_ASM_KCONST, kcc = what & GLIMS_ASM_KCC;
+    i64 ns = c->pat.n_slots;
+    if (res) {
+        GL_CUDA(cudaMemsetAsync(c->F, 0, sizeof(double) * c->ndof, c->stream));
+    }
+    bool gather = (variant == GLIMS_ASMK_GATHER) && (kconst || kcc);
+    if (gather) {
+        build_gather_map(c);
+        int g = nblk(ns, 128);
+#define GATHER(KC, KK) k_assemble_gather<D, KC, KK><<<g, 128, 0, c->stream>>>(c->coords, c->cells, c->cell_mat, c->mat, \
+            c->n_mat, c->dt, c->x, c->gptr, c->gent, ns, c->Kuu, c->Kuc, c->Kcc)
+        if (kconst && kcc) GATHER(true, true); else if (kconst) GATHER(true, false); else GATHER(false, true);
+#undef GATHER
+        LAUNCHED(c);
+        if (!res) return;
+    } else {
+        if (kconst) {
+            GL_CUDA(cudaMemsetAsync(c->Kuu, 0, sizeof(double) * ns * D * D, c->stream));
+            GL_CUDA(cudaMemsetAsync(c->Kuc, 0, sizeof(double) * ns * D, c->stream));
+        }
+        if (kcc) GL_CUDA(cudaMemsetAsync(c->Kcc, 0, sizeof(double) * ns, c->stream));
+    }
+    int g = nblk(c->n_c, 128);
+#define ATOMIC(R, KC, KK) k_assemble_atomic<D, R, KC, KK><<<g, 128, 0, c->stream>>>(c->coords, c->cells, c->cell_mat, \
+        c->mat, c->n_mat, c->n_c, n_own, c->dt, c->x, c->xprev, c->eslot, c->F, c->Kuu, c->Kuc, c->Kcc)
+    bool akc = kconst && !gather, akk = kcc && !gather;
+    if (res && akc && akk) ATOMIC(true, true, true);
+    else if (res && akc) ATOMIC(true, true, false);
+    else if (res && akk) ATOMIC(true, false, true);
+    else if (res) ATOMIC(true, false, false);
+    else if (akc && akk) ATOMIC(false, true, true);
+    else if (akc) ATOMIC(false, true, false);
+    else if (akk) ATOMIC(false, false, true);
+#undef ATOMIC
+    LAUNCHED(c);
+    if (res && c->have_load) {
+        k_sub<<<red_grid(c, c->ndof), TPB, 0, c->stream>>>(c->F, c->fext, (i64)c->pat.n_rows * NB);
+        LAUNCHED(c);
+    }
+    (void)NB;
+}
+
+void launch_assemble(glims_ctx* c, int what, int variant) {
+    if (c->dim == 2) assemble_dim<2>(c, what, variant); else assemble_dim<3>(c, what, variant);
+    GL_CUDA(cudaGetLastError());
+}
+
+void launch_bc_values(glims_ctx* c, double* x) {
+    if (!c->n_bc) return;
+    k_bc_values<<<nblk(c->n_bc), TPB, 0, c->stream>>>(c->bc_dofs, c->bc_vals, c->n_bc, x);
+    LAUNCHED(c);
+}
+void launch_bc_residual(glims_ctx* c, double* F, const double* x) {
+    if (!c->n_bc) return;
+    k_bc_residual<<<nblk(c->n_bc), TPB, 0, c->stream>>>(c->bc_dofs, c->bc_vals, c->n_bc, x, F);
+    LAUNCHED(c);
+}
+void launch_bc_matrix(glims_ctx* c, int what, bool sym) {
+    if (!c->n_bc) return;
+    // skip the launch when no Dirichlet dof touches the requested blocks
+    if (!(what & GLIMS_ASM_KCONST) && c->n_bc_c == 0) return;
+    auto& p = c->pat;
+    if (c->dim == 2) {
+        k_bc_matrix<2><<<p.n_slices, 128, 0, c->stream>>>(c->bcmask, p.slice_off, p.slice_w, p.col, p.n_rows, what, sym, c->Kuu, c->Kuc, c->Kcc);
+        k_bc_diag<2><<<nblk(c->n_bc), TPB, 0, c->stream>>>(c->bc_dofs, c->n_bc, p.n_rows, p.diag, what, c->Kuu, c->Kcc);
+    } else {
+        k_bc_matrix<3><<<p.n_slices, 128, 0, c->stream>>>(c->bcmask, p.slice_off, p.slice_w, p.col, p.n_rows, what, sym, c->Kuu, c->Kuc, c->Kcc);
+        k_bc_diag<3><<<nblk(c->n_bc), TPB, 0, c->stream>>>(c->bc_dofs, c->n_bc, p.n_rows, p.diag, what, c->Kuu, c->Kcc);
+    }
+    c->launches += 2;
+}
+void launch_diag_inverse(glims_ctx* c, int which) {
+    auto& p = c->pat;
+    double* out = which == 0 ? c->dinv_mono : which == 1 ? c->dinv_uu : c->dinv_cc;
+    if (c->dim == 2) k_diag_inverse<2><<<nblk(p.n_rows), TPB, 0, c->stream>>>(p.diag, p.n_rows, which, c->Kuu, c->Kuc, c->Kcc, out);
+    else k_diag_inverse<3><<<nblk(p.n_rows), TPB, 0, c->stream>>>(p.diag, p.n_rows, which, c->Kuu, c->Kuc, c->Kcc, out);
+    LAUNCHED(c);
+}
+void launch_export_values(glims_ctx* c, double* Kuu, double* Kuc, double* Kcc) {
+    auto& p = c->pat;
+    int g = nblk(p.n_rows);
+    if (c->dim == 2) {
+        k_export<4><<<g, TPB, 0, c->stream>>>(p.rowptr, p.slice_off, p.n_rows, c->Kuu, Kuu);
+        k_export<2><<<g, TPB, 0, c->stream>>>(p.rowptr, p.slice_off, p.n_rows, c->Kuc, Kuc);
+    } else {
+        k_export<9><<<g, TPB, 0, c->stream>>>(p.rowptr, p.slice_off, p.n_rows, c->Kuu, Kuu);
+        k_export<3><<<g, TPB, 0, c->stream>>>(p.rowptr, p.slice_off, p.n_rows, c->Kuc, Kuc);
+    }
+    k_export<1><<<g, TPB, 0, c->stream>>>(p.rowptr, p.slice_off, p.n_rows, c->Kcc, Kcc);
+    c->launches += 3;
+}
+
+void launch_spmv(glims_ctx* c, int which, const double* x, double* y, SpmvDot dot) {
+    auto& p = c->pat;
+    int g = red_grid(c, p.n_rows);
+    bool d = dot.w != nullptr;
+#define ARGS p.n_rows, dot.w, c->partials, c->tickets, c->scal, dot.slot
+    if (which == 0) {
+        if (c->dim == 2) { if (d) k_spmv_mono<2, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, c->Kcc, x, y, ARGS);
+                           else k_spmv_mono<2, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, c->Kcc, x, y, ARGS); }
+        else             { if (d) k_spmv_mono<3, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, c->Kcc, x, y, ARGS);
+                           else k_spmv_mono<3, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, c->Kcc, x, y, ARGS); }
+    } else if (which == 1) {
+        if (c->dim == 2) { if (d) k_spmv_block<2, 2, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS);
+                           else k_spmv_block<2, 2, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS); }
+        else             { if (d) k_spmv_block<3, 3, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS);
+                           else k_spmv_block<3, 3, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS); }
+    } else {
+        if (d) k_spmv_block<1, 1, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kcc, x, y, ARGS);
+        else k_spmv_block<1, 1, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kcc, x, y, ARGS);
+    }
+#undef ARGS
+    LAUNCHED(c);
+}
+void launch_spmv_uc(glims_ctx* c, const double* xc, double* yu) {
+    auto& p = c->pat;
+    if (c->dim == 2) k_spmv_uc<2><<<nblk(p.n_slices * 32), TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuc, xc, yu, p.n_rows);
+    else k_spmv_uc<3><<<nblk(p.n_slices * 32), TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuc, xc, yu, p.n_rows);
+    LAUNCHED(c);
+}
+void launch_spmv_generic(glims_ctx* c, const SellPattern& p, const double* A, int bs, const double* x, double* y) {
+    int g = red_grid(c, p.n_rows);
+#define GEN(B) k_spmv_block<B, B, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, nullptr, c->partials, c->tickets, c->scal, 0)
+    if (bs == 1) GEN(1); else if (bs == 2) GEN(2); else if (bs == 3) GEN(3); else if (bs == 6) GEN(6);
+    else throw GlError(GLIMS_ERR_ARG, "spmv_generic: unsupported block size");
+#undef GEN
+    LAUNCHED(c);
+}
+
+void launch_dot(glims_ctx* c, const double* a, const double* b, i64 n, int slot) {
+    k_dot<<<red_grid(c, n), TPB, 0, c->stream>>>(a, b, n, c->partials, c->tickets, c->scal, slot);
+    LAUNCHED(c);
+}
+void launch_multi_dot(glims_ctx* c, const double* V, i64 ld, int k, const double* w, i64 n, int slot0) {
+    k_multi_dot<<<red_grid(c, n), TPB, 0, c->stream>>>(V, ld, k, w, n, c->partials, c->tickets, c->scal, slot0);
+    LAUNCHED(c);
+}
+void launch_multi_axpy(glims_ctx* c, const double* V, i64 ld, int k, const double* coef_dev, double sign, double* w, i64 n) {
+    k_multi_axpy<<<red_grid(c, n), TPB, 0, c->stream>>>(V, ld, k, coef_dev, sign, w, n);
+    LAUNCHED(c);
+}
+void launch_axpy(glims_ctx* c, double alpha, const double* x, double* y, i64 n) {
+    k_axpy<<<red_grid(c, n), TPB, 0, c->stream>>>(alpha, x, y, n);
+    LAUNCHED(c);
+}
+void launch_scale(glims_ctx* c, double alpha, double* x, i64 n) {
+    k_scale<<<red_grid(c, n), TPB, 0, c->stream>>>(alpha, x, n);
+    LAUNCHED(c);
+}
+void launch_copy(glims_ctx* c, const double* x, double* y, i64 n) {
+    GL_CUDA(cudaMemcpyAsync(y, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+}
+void launch_zero(glims_ctx* c, double* x, i64 n) { GL_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, c->stream)); }
+void launch_cg_update_xr(glims_ctx* c, double* x, double* r, const double* p, const double* Ap, i64 n, int s_num,
+                         int s_den, int s_rr) {
+    k_cg_update_xr<<<red_grid(c, n), TPB, 0, c->stream>>>(x, r, p, Ap, n, s_num, s_den, s_rr, c->partials, c->tickets, c->scal);
+    LAUNCHED(c);
+}
+void launch_cg_update_p(glims_ctx* c, double* p, const double* z, i64 n, int s_num, int s_den) {
+    k_cg_update_p<<<red_grid(c, n), TPB, 0, c->stream>>>(p, z, n, s_num, s_den, c->scal);
+    LAUNCHED(c);
+}
+void launch_block_jacobi(glims_ctx* c, const double* dinv, int bs, const double* r, double* z, i64 n_rows, int s_rz) {
+    int g = red_grid(c, n_rows);
+#define BJ(B) k_block_jacobi<B><<<g, TPB, 0, c->stream>>>(dinv, r, z, n_rows, c->partials, c->tickets, c->scal, s_rz)
+    if (bs == 1) BJ(1); else if (bs == 2) BJ(2); else if (bs == 3) BJ(3); else if (bs == 4) BJ(4); else if (bs == 6) BJ(6);
+    else throw GlError(GLIMS_ERR_ARG, "block_jacobi: unsupported block size");
+#undef BJ
+    LAUNCHED(c);
+}
+void launch_extract(glims_ctx* c, const double* xb, double* xu, double* xc) {
+    i64 n = c->pat.n_rows;
+    if (c->dim == 2) k_extract<2><<<red_grid(c, n), TPB, 0, c->stream>>>(xb, xu, xc, n);
+    else k_extract<3><<<red_grid(c, n), TPB, 0, c->stream>>>(xb, xu, xc, n);
+    LAUNCHED(c);
+}
+void launch_insert_add(glims_ctx* c, double* xb, const double* du, const double* dc, double alpha) {
+    i64 n = c->pat.n_rows;
+    if (c->dim == 2) k_insert_add<2><<<red_grid(c, n), TPB, 0, c->stream>>>(xb, du, dc, alpha, n);
+    else k_insert_add<3><<<red_grid(c, n), TPB, 0, c->stream>>>(xb, du, dc, alpha, n);
+    LAUNCHED(c);
+}
+void launch_split_norms(glims_ctx* c, const double* F, int s0) {
+    i64 n = c->pat.n_rows;
+    if (c->dim == 2) k_split_norms<2><<<red_grid(c, n), TPB, 0, c->stream>>>(F, n, c->partials, c->tickets, c->scal, s0);
+    else k_split_norms<3><<<red_grid(c, n), TPB, 0, c->stream>>>(F, n, c->partials, c->tickets, c->scal, s0);
+    LAUNCHED(c);
+}
+void read_scalars(glims_ctx* c, int slot0, int n, double* out) {
+    GL_CUDA(cudaMemcpyAsync(c->h_scal + slot0, c->scal + slot0, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) out[i] = c->h_scal[slot0 + i];
+}
+void flush_l2(glims_ctx* c) {
+    if (!c->flush_buf) {
+        c->flush_bytes = (size_t)256 << 20;   // 256 MiB > 126 MB L2
+        GL_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    k_flush<<<148 * 8, TPB, 0, c->stream>>>((double*)c->flush_buf, (i64)(c->flush_bytes / 8));
+}

@@ -1,0 +1,584 @@
+// Host drivers: context life cycle, C ABI, Krylov solvers with device-resident scalars,
+// Newton loop (SNES newtonls/basic semantics) and the backward-Euler step.
+#include "common.h"
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+#include <map>
+
+void launch_split_norms(glims_ctx* c, const double* F, int s0);
+
+namespace {
+
+struct Pool { std::map<std::string, std::pair<double*, i64>> m; };
+std::map<glims_ctx*, Pool> g_pools;
+
+double* ws(glims_ctx* c, const char* name, i64 n) {
+    auto& e = g_pools[c].m[name];
+    if (e.second < n) {
+        if (e.first) cudaFree(e.first);
+        GL_CUDA(cudaMalloc(&e.first, sizeof(double) * (n > 0 ? n : 1)));
+        GL_CUDA(cudaMemsetAsync(e.first, 0, sizeof(double) * (n > 0 ? n : 1), c->stream));
+        e.second = n;
+    }
+    return e.first;
+}
+void free_pool(glims_ctx* c) {
+    for (auto& kv : g_pools[c].m) cudaFree(kv.second.first);
+    g_pools.erase(c);
+}
+
+struct EvTimer {           // accumulates device time of bracketed segments on the stream
+    cudaStream_t st;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> segs[3];   // 0 total, 1 assembly, 2 krylov
+    explicit EvTimer(cudaStream_t s) : st(s) {}
+    void begin(int k) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        segs[k].push_back({a, b});
+    }
+    void end(int k) { cudaEventRecord(segs[k].back().second, st); }
+    float total(int k) {
+        float t = 0;
+        for (auto& p : segs[k]) { float ms = 0; cudaEventSynchronize(p.second); cudaEventElapsedTime(&ms, p.first, p.second); t += ms; }
+        return t;
+    }
+    ~EvTimer() { for (auto& s : segs) for (auto& p : s) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
+};
+
+template <class T> T* dev_upload(const T* h, i64 n, cudaStream_t st) {
+    T* d = nullptr;
+    GL_CUDA(cudaMalloc(&d, sizeof(T) * (n > 0 ? n : 1)));
+    if (n > 0) GL_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+    return d;
+}
+
+i64 nrows(glims_ctx* c) { return c->pat.n_rows; }
+
+// ------------------------------------------------------------------------------------------------
+// preconditioner application z = M^-1 r, rz -> slot
+void apply_pc(glims_ctx* c, int which, int pc, const double* r, double* z, int s_rz) {
+    if (which == 2) { launch_block_jacobi(c, c->dinv_cc, 1, r, z, nrows(c), s_rz); return; }
+    if (which == 1) {
+        if (pc == GLIMS_PC_AMG && c->amg) {
+            amg_vcycle(c, r, z);
+            launch_dot(c, r, z, nrows(c) * c->dim, s_rz);
+        } else launch_block_jacobi(c, c->dinv_uu, c->dim, r, z, nrows(c), s_rz);
+        return;
+    }
+    launch_block_jacobi(c, c->dinv_mono, c->nb, r, z, nrows(c), s_rz);
+}
+
+// PCG on block `which` (1: K_uu, 2: K_cc), zero initial guess. Returns iterations, or -1 if not converged.
+int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_rel, double scale, double tol_abs,
+        int maxit, double* res_out) {
+    const int bs = which == 1 ? c->dim : 1;
+    const i64 n = nrows(c) * bs, nl = c->n_v * bs;
+    const char* tag = which == 1 ? "u" : "c";
+    char nm[32];
+    auto W = [&](const char* base) { snprintf(nm, sizeof nm, "cg_%s_%s", base, tag); return ws(c, nm, nl); };
+    double *r = W("r"), *p = W("p"), *Ap = W("Ap"), *z = W("z");
+    launch_copy(c, b, r, n);
+    launch_zero(c, x, n);
+    launch_dot(c, b, b, n, S_BN);
+    allreduce_scalars(c, S_BN, 1);
+    double bn2;
+    read_scalars(c, S_BN, 1, &bn2);
+    double bn = std::sqrt(bn2);
+    if (scale <= 0) scale = bn;
+    double tol = std::max(tol_rel * scale, tol_abs);
+    if (res_out) *res_out = bn;
+    if (bn <= tol || bn == 0.0) return 0;
+    int cur = S_RZ, nxt = S_RZNEW;
+    apply_pc(c, which, pc, r, z, cur);
+    allreduce_scalars(c, cur, 1);
+    launch_copy(c, z, p, n);
+    cudaEvent_t ev[2];
+    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    double* h_rr = c->h_scal + S_COUNT;   // two pinned slots after the mirror
+    int result = -1;
+    for (int it = 1; it <= maxit + 1; ++it) {
+        if (it <= maxit) {
+            halo_exchange(c, p, bs);
+            SpmvDot d; d.w = p; d.slot = S_PAP;
+            launch_spmv(c, which, p, Ap, d);
+            allreduce_scalars(c, S_PAP, 1);
+            launch_cg_update_xr(c, x, r, p, Ap, n, cur, S_PAP, S_RR);
+            apply_pc(c, which, pc, r, z, nxt);
+            allreduce_scalars(c, S_RR, 1);
+            allreduce_scalars(c, nxt, 1);
+            GL_CUDA(cudaMemcpyAsync(&h_rr[it & 1], c->scal + S_RR, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            GL_CUDA(cudaEventRecord(ev[it & 1], c->stream));
+            launch_cg_update_p(c, p, z, n, nxt, cur);
+            std::swap(cur, nxt);
+        }
+        if (it >= 2) {   // inspect the previous iteration while this one is already queued
+            GL_CUDA(cudaEventSynchronize(ev[(it - 1) & 1]));
+            double rn = std::sqrt(h_rr[(it - 1) & 1]);
+            if (res_out) *res_out = rn;
+            if (!(rn == rn)) { result = -1; break; }
+            if (rn <= tol) { result = std::min(it, maxit); break; }
+        }
+    }
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    return result;
+}
+
+// Right-preconditioned restarted GMRES(m) on the monolithic Jacobian, block-Jacobi PC, zero initial guess.
+int gmres_mono(glims_ctx* c, const double* b, double* x, double tol, int maxit, double* res_out) {
+    const int m = 30;
+    const i64 n = nrows(c) * c->nb, nl = c->n_v * c->nb;
+    double* V = ws(c, "gm_V", nl * (m + 1));
+    double* w = ws(c, "gm_w", nl);
+    double* z = ws(c, "gm_z", nl);
+    double* coef = ws(c, "gm_coef", 64);
+    launch_zero(c, x, n);
+    std::vector<double> H((m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
+    int total = 0;
+    bool first = true;
+    double beta = 0;
+    while (total < maxit) {
+        // r = b - A x
+        if (first) launch_copy(c, b, w, n);
+        else {
+            halo_exchange(c, x, c->nb);
+            launch_spmv(c, 0, x, w);
+            launch_scale(c, -1.0, w, n);
+            launch_axpy(c, 1.0, b, w, n);
+        }
+        launch_dot(c, w, w, n, S_TMP0);
+        allreduce_scalars(c, S_TMP0, 1);
+        double b2; read_scalars(c, S_TMP0, 1, &b2);
+        beta = std::sqrt(b2);
+        if (res_out) *res_out = beta;
+        if (beta <= tol) return total;
+        first = false;
+        launch_copy(c, w, V, n);
+        launch_scale(c, 1.0 / beta, V, n);
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = beta;
+        int j = 0;
+        for (; j < m && total < maxit; ++j, ++total) {
+            launch_block_jacobi(c, c->dinv_mono, c->nb, V + (i64)j * nl, z, nrows(c), -1);
+            halo_exchange(c, z, c->nb);
+            launch_spmv(c, 0, z, w);
+            // classical Gram-Schmidt, twice (CGS2): batched dots then one fused update
+            std::vector<double> h(j + 2, 0.0), h2(j + 1);
+            for (int pass = 0; pass < 2; ++pass) {
+                launch_multi_dot(c, V, nl, j + 1, w, n, S_GM0);
+                allreduce_scalars(c, S_GM0, j + 1);
+                GL_CUDA(cudaMemcpyAsync(coef, c->scal + S_GM0, sizeof(double) * (j + 1), cudaMemcpyDeviceToDevice, c->stream));
+                launch_multi_axpy(c, V, nl, j + 1, coef, -1.0, w, n);
+                read_scalars(c, S_GM0, j + 1, h2.data());
+                for (int i = 0; i <= j; ++i) h[i] += h2[i];
+            }
+            launch_dot(c, w, w, n, S_TMP0);
+            allreduce_scalars(c, S_TMP0, 1);
+            double w2; read_scalars(c, S_TMP0, 1, &w2);
+            h[j + 1] = std::sqrt(w2);
+            launch_copy(c, w, V + (i64)(j + 1) * nl, n);
+            if (h[j + 1] > 0) launch_scale(c, 1.0 / h[j + 1], V + (i64)(j + 1) * nl, n);
+            for (int i = 0; i < j; ++i) {
+                double t = cs[i] * h[i] + sn[i] * h[i + 1];
+                h[i + 1] = -sn[i] * h[i] + cs[i] * h[i + 1];
+                h[i] = t;
+            }
+            double den = std::hypot(h[j], h[j + 1]);
+            cs[j] = den > 0 ? h[j] / den : 1.0;
+            sn[j] = den > 0 ? h[j + 1] / den : 0.0;
+            h[j] = den;
+            g[j + 1] = -sn[j] * g[j];
+            g[j] = cs[j] * g[j];
+            for (int i = 0; i <= j; ++i) H[i * m + j] = h[i];
+            if (res_out) *res_out = std::fabs(g[j + 1]);
+            if (std::fabs(g[j + 1]) <= tol) { ++j; ++total; break; }
+        }
+        // y = H^-1 g ; x += M^-1 (V y)
+        for (int i = j - 1; i >= 0; --i) {
+            double s = g[i];
+            for (int k = i + 1; k < j; ++k) s -= H[i * m + k] * y[k];
+            y[i] = s / H[i * m + i];
+        }
+        GL_CUDA(cudaMemcpyAsync(coef, y.data(), sizeof(double) * j, cudaMemcpyHostToDevice, c->stream));
+        GL_CUDA(cudaStreamSynchronize(c->stream));
+        launch_zero(c, w, n);
+        launch_multi_axpy(c, V, nl, j, coef, 1.0, w, n);
+        launch_block_jacobi(c, c->dinv_mono, c->nb, w, z, nrows(c), -1);
+        launch_axpy(c, 1.0, z, x, n);
+        if (std::fabs(g[j]) <= tol && j <= m) {
+            if (res_out) *res_out = std::fabs(g[j]);
+            return total;
+        }
+    }
+    return -1;
+}
+
+void ensure_kconst(glims_ctx* c, const glims_solver_opts* o) {
+    bool need_amg = (o->pc == GLIMS_PC_AMG) && o->solver == GLIMS_SOLVER_BLOCK_TRI;
+    if (!c->kconst_valid) {
+        launch_assemble(c, GLIMS_ASM_KCONST, o->asm_kernel);
+        launch_bc_matrix(c, GLIMS_ASM_KCONST, true);
+        launch_diag_inverse(c, 1);
+        c->kconst_valid = true;
+        if (c->amg) amg_free(c);
+    }
+    if (need_amg && !c->amg) amg_setup(c);
+}
+
+void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st) {
+    EvTimer tm(c->stream);
+    tm.begin(0);
+    const int D = c->dim, NB = c->nb;
+    const i64 nr = nrows(c);
+    ensure_kconst(c, o);
+    launch_bc_values(c, c->x);
+    double *Fu = ws(c, "Fu", c->n_v * D), *Fc = ws(c, "Fc", c->n_v);
+    double *du = ws(c, "du", c->n_v * D), *dc = ws(c, "dc", c->n_v), *tmpu = ws(c, "tmpu", c->n_v * D);
+    glims_step_stats s;
+    memset(&s, 0, sizeof s);
+    double f0 = -1, fu_scale = 0, T = 0;
+    bool converged = false, c_was_done = false;
+    for (int k = 0; k <= o->max_newton; ++k) {
+        tm.begin(1);
+        halo_exchange(c, c->x, NB);
+        // one pass over the elements: residual, plus K_cc while the concentration block is still iterating
+        const bool with_kcc = o->solver == GLIMS_SOLVER_MONO_GMRES || !(o->lag_mechanics && c_was_done);
+        launch_assemble(c, GLIMS_ASM_RESIDUAL | (with_kcc ? GLIMS_ASM_KCC : 0), o->asm_kernel);
+        launch_bc_residual(c, c->F, c->x);
+        launch_split_norms(c, c->F, S_TMP0);
+        allreduce_scalars(c, S_TMP0, 2);
+        tm.end(1);
+        double nn[2];
+        read_scalars(c, S_TMP0, 2, nn);
+        double fu = std::sqrt(nn[0]), fc = std::sqrt(nn[1]), fn = std::sqrt(nn[0] + nn[1]);
+        if (!(fn == fn)) throw GlError(GLIMS_ERR_NOT_CONVERGED, "Newton: residual is NaN");
+        if (k == 0) {
+            f0 = fn; s.fnorm0 = fn;
+            T = std::max(o->snes_rtol * f0, o->snes_atol);
+            // scale for the mechanics tolerance: |f_ext_u - K_uc c| or the first |F_u|, whichever is larger
+            launch_extract(c, c->x, nullptr, dc);
+            halo_exchange(c, dc, 1);
+            launch_spmv_uc(c, dc, tmpu);
+            launch_dot(c, tmpu, tmpu, nr * D, S_TMP2);
+            allreduce_scalars(c, S_TMP2, 1);
+            double bu2; read_scalars(c, S_TMP2, 1, &bu2);
+            fu_scale = std::max(std::sqrt(bu2), fu);
+        }
+        s.fnorm = fn;
+        s.newton_its = k;
+        if (fn < o->snes_atol || fn <= o->snes_rtol * f0) { converged = true; break; }
+        if (k == o->max_newton) break;
+
+        tm.begin(2);
+        if (o->solver == GLIMS_SOLVER_MONO_GMRES) {
+            launch_bc_matrix(c, GLIMS_ASM_KCC, true);
+            launch_diag_inverse(c, 0);
+            double* rhs = ws(c, "rhs_mono", c->ndof);
+            launch_copy(c, c->F, rhs, nr * NB);
+            launch_scale(c, -1.0, rhs, nr * NB);
+            double res = 0;
+            int its = gmres_mono(c, rhs, c->dx, std::max(o->ksp_rtol * fn, o->ksp_atol), o->max_krylov, &res);
+            if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "GMRES did not converge");
+            s.krylov_its_mono += its;
+            launch_axpy(c, 1.0, c->dx, c->x, nr * NB);
+        } else {
+            launch_extract(c, c->F, Fu, Fc);
+            const bool c_done = fc <= 0.5 * T;
+            c_was_done = c_was_done || c_done;
+            const bool solve_c = fc > 0.0 && (!c_done || !o->lag_mechanics);
+            const bool solve_u_now = c_done || !o->lag_mechanics;
+            if (solve_c && !with_kcc) launch_assemble(c, GLIMS_ASM_KCC, o->asm_kernel);
+            if (solve_c) {
+                launch_bc_matrix(c, GLIMS_ASM_KCC, true);
+                launch_diag_inverse(c, 2);
+                launch_scale(c, -1.0, Fc, nr);
+                double res = 0;
+                int its = pcg(c, 2, GLIMS_PC_JACOBI, Fc, dc, o->ksp_rtol, fc, o->ksp_atol, o->max_krylov, &res);
+                if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "PCG on K_cc did not converge");
+                s.krylov_its_c += its;
+            } else launch_zero(c, dc, nr);
+            if (solve_u_now && fu > 0.0) {
+                // rhs_u = -F_u - K_uc dc
+                if (solve_c) {
+                    halo_exchange(c, dc, 1);
+                    launch_spmv_uc(c, dc, tmpu);
+                    launch_axpy(c, 1.0, tmpu, Fu, nr * D);
+                }
+                launch_scale(c, -1.0, Fu, nr * D);
+                double res = 0;
+                int its = pcg(c, 1, o->pc, Fu, du, o->ksp_rtol, fu_scale, o->ksp_atol, o->max_krylov, &res);
+                if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "PCG on K_uu did not converge");
+                s.krylov_its_u += its;
+                launch_insert_add(c, c->x, du, dc, 1.0);
+            } else launch_insert_add(c, c->x, nullptr, dc, 1.0);
+        }
+        tm.end(2);
+    }
+    tm.end(0);
+    s.converged = converged;
+    s.ms_total = tm.total(0);
+    s.ms_assembly = tm.total(1);
+    s.ms_krylov = tm.total(2);
+    if (st) *st = s;
+    if (!converged) throw GlError(GLIMS_ERR_NOT_CONVERGED, "Newton did not converge");
+}
+
+}  // namespace
+
+// ================================================================================================
+#define API_BEGIN if (!c) return GLIMS_ERR_ARG; try { GL_CUDA(cudaSetDevice(c->device));
+#define API_END } catch (const GlError& e) { c->err = e.msg; return e.code; } catch (const std::exception& e) { c->err = e.what(); return GLIMS_ERR_CUDA; } return GLIMS_OK;
+
+extern "C" {
+
+void glims_default_opts(glims_solver_opts* o) {
+    o->snes_rtol = 1e-9; o->snes_atol = 1e-10; o->snes_stol = 1e-16; o->max_newton = 50;
+    o->ksp_rtol = 1e-10; o->ksp_atol = 1e-300; o->max_krylov = 20000;
+    o->solver = GLIMS_SOLVER_BLOCK_TRI; o->pc = GLIMS_PC_AMG; o->asm_kernel = GLIMS_ASMK_ATOMIC;
+    o->lag_mechanics = 1;
+}
+
+int glims_create(glims_ctx** out, int32_t dim, int64_t n_vertices, const double* coords, int64_t n_cells,
+                 const int32_t* cells, const int32_t* cell_mat, int64_t n_owned, int32_t device) {
+    if (!out || (dim != 2 && dim != 3) || n_vertices <= 0 || n_cells <= 0 || !coords || !cells || !cell_mat)
+        return GLIMS_ERR_ARG;
+    glims_ctx* c = new glims_ctx();
+    *out = c;
+    c->device = device;
+    API_BEGIN
+    c->dim = dim; c->nb = dim + 1; c->n_v = n_vertices; c->n_c = n_cells; c->ndof = n_vertices * c->nb;
+    if (n_owned >= 0 && n_owned < n_vertices) { c->halo.active = true; c->halo.n_owned = n_owned; }
+    GL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->coords = dev_upload(coords, n_vertices * dim, c->stream);
+    c->cells = dev_upload(cells, n_cells * c->nb, c->stream);
+    c->cell_mat = dev_upload(cell_mat, n_cells, c->stream);
+    GL_CUDA(cudaMalloc(&c->scal, sizeof(double) * S_COUNT));
+    GL_CUDA(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_COUNT, c->stream));
+    GL_CUDA(cudaMalloc(&c->partials, sizeof(double) * S_COUNT * 148 * 8));
+    GL_CUDA(cudaMalloc(&c->tickets, sizeof(unsigned) * S_COUNT));
+    GL_CUDA(cudaMemsetAsync(c->tickets, 0, sizeof(unsigned) * S_COUNT, c->stream));
+    GL_CUDA(cudaMallocHost(&c->h_scal, sizeof(double) * (S_COUNT + 8)));
+    build_pattern(c);
+    i64 ns = c->pat.n_slots;
+    GL_CUDA(cudaMalloc(&c->Kuu, sizeof(double) * ns * dim * dim));
+    GL_CUDA(cudaMalloc(&c->Kuc, sizeof(double) * ns * dim));
+    GL_CUDA(cudaMalloc(&c->Kcc, sizeof(double) * ns));
+    GL_CUDA(cudaMemsetAsync(c->Kuu, 0, sizeof(double) * ns * dim * dim, c->stream));
+    GL_CUDA(cudaMemsetAsync(c->Kuc, 0, sizeof(double) * ns * dim, c->stream));
+    GL_CUDA(cudaMemsetAsync(c->Kcc, 0, sizeof(double) * ns, c->stream));
+    i64 nr = c->pat.n_rows;
+    GL_CUDA(cudaMalloc(&c->dinv_uu, sizeof(double) * nr * dim * dim));
+    GL_CUDA(cudaMalloc(&c->dinv_cc, sizeof(double) * nr));
+    GL_CUDA(cudaMalloc(&c->dinv_mono, sizeof(double) * nr * c->nb * c->nb));
+    for (double** v : {&c->x, &c->xprev, &c->F, &c->fext, &c->dx}) {
+        GL_CUDA(cudaMalloc(v, sizeof(double) * c->ndof));
+        GL_CUDA(cudaMemsetAsync(*v, 0, sizeof(double) * c->ndof, c->stream));
+    }
+    GL_CUDA(cudaMalloc(&c->bcmask, c->n_v));
+    GL_CUDA(cudaMemsetAsync(c->bcmask, 0, c->n_v, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_destroy(glims_ctx* c) {
+    if (!c) return GLIMS_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->amg) amg_free(c);
+    free_pool(c);
+    auto& p = c->pat;
+    for (void* q : {(void*)c->coords, (void*)c->cells, (void*)c->cell_mat, (void*)c->mat, (void*)p.slice_off,
+                    (void*)p.slice_w, (void*)p.col, (void*)p.rowptr, (void*)p.diag, (void*)c->eslot, (void*)c->gptr,
+                    (void*)c->gent, (void*)c->Kuu, (void*)c->Kuc, (void*)c->Kcc, (void*)c->dinv_uu, (void*)c->dinv_cc,
+                    (void*)c->dinv_mono, (void*)c->x, (void*)c->xprev, (void*)c->F, (void*)c->fext, (void*)c->dx,
+                    (void*)c->bc_dofs, (void*)c->bc_vals, (void*)c->bcmask, (void*)c->scal, (void*)c->partials,
+                    (void*)c->tickets, (void*)c->flush_buf, (void*)c->halo.send_idx, (void*)c->halo.send_buf})
+        if (q) cudaFree(q);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return GLIMS_OK;
+}
+
+const char* glims_last_error(const glims_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int glims_set_materials(glims_ctx* c, int32_t n_mat, const double* table) {
+    API_BEGIN
+    if (n_mat <= 0 || n_mat > MAX_MAT || !table) throw GlError(GLIMS_ERR_ARG, "set_materials: need 1..64 rows");
+    std::vector<double> t(n_mat * MAT_STRIDE);
+    for (int m = 0; m < n_mat; ++m) {
+        for (int k = 0; k < 5; ++k) t[m * MAT_STRIDE + k] = table[m * 5 + k];
+        t[m * MAT_STRIDE + 5] = (2.0 * table[m * 5 + 0] + c->dim * table[m * 5 + 1]) * table[m * 5 + 4];
+    }
+    if (c->mat) cudaFree(c->mat);
+    c->mat = dev_upload(t.data(), (i64)t.size(), c->stream);
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_mat = n_mat; c->have_mat = true; c->kconst_valid = false;
+    API_END
+}
+
+int glims_set_dt(glims_ctx* c, double dt) { if (!c) return GLIMS_ERR_ARG; c->dt = dt; return GLIMS_OK; }
+
+int glims_set_dirichlet(glims_ctx* c, int64_t n, const int64_t* dofs, const double* vals) {
+    API_BEGIN
+    if (n < 0 || (n > 0 && (!dofs || !vals))) throw GlError(GLIMS_ERR_ARG, "set_dirichlet: bad arguments");
+    if (c->bc_dofs) { cudaFree(c->bc_dofs); c->bc_dofs = nullptr; }
+    if (c->bc_vals) { cudaFree(c->bc_vals); c->bc_vals = nullptr; }
+    std::vector<unsigned char> mask(c->n_v, 0);
+    c->n_bc_u = c->n_bc_c = 0;
+    for (i64 t = 0; t < n; ++t) {
+        if (dofs[t] < 0 || dofs[t] >= c->ndof) throw GlError(GLIMS_ERR_ARG, "set_dirichlet: dof out of range");
+        i64 v = dofs[t] / c->nb; int k = (int)(dofs[t] - v * c->nb);
+        mask[v] |= (unsigned char)(1u << k);
+        if (k < c->dim) c->n_bc_u++; else c->n_bc_c++;
+    }
+    c->n_bc = n;
+    if (n > 0) {
+        c->bc_dofs = dev_upload((const i64*)dofs, n, c->stream);
+        c->bc_vals = dev_upload(vals, n, c->stream);
+    }
+    GL_CUDA(cudaMemcpyAsync(c->bcmask, mask.data(), c->n_v, cudaMemcpyHostToDevice, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    c->kconst_valid = false;
+    API_END
+}
+
+int glims_set_load(glims_ctx* c, const double* f_ext) {
+    API_BEGIN
+    c->have_load = f_ext != nullptr;
+    if (f_ext) {
+        GL_CUDA(cudaMemcpyAsync(c->fext, f_ext, sizeof(double) * c->ndof, cudaMemcpyHostToDevice, c->stream));
+        GL_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    API_END
+}
+
+static int copy_vec(glims_ctx* c, double* dev, double* host_out, const double* host_in) {
+    API_BEGIN
+    if (host_in) GL_CUDA(cudaMemcpyAsync(dev, host_in, sizeof(double) * c->ndof, cudaMemcpyHostToDevice, c->stream));
+    if (host_out) GL_CUDA(cudaMemcpyAsync(host_out, dev, sizeof(double) * c->ndof, cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+int glims_set_state(glims_ctx* c, const double* x) { return x ? copy_vec(c, c ? c->x : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
+int glims_get_state(glims_ctx* c, double* x) { return x ? copy_vec(c, c ? c->x : nullptr, x, nullptr) : GLIMS_ERR_ARG; }
+int glims_set_prev(glims_ctx* c, const double* x) { return x ? copy_vec(c, c ? c->xprev : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
+int glims_get_prev(glims_ctx* c, double* x) { return x ? copy_vec(c, c ? c->xprev : nullptr, x, nullptr) : GLIMS_ERR_ARG; }
+int64_t glims_ndof(const glims_ctx* c) { return c ? c->ndof : 0; }
+int64_t glims_nnzb(const glims_ctx* c) { return c ? c->pat.nnzb : 0; }
+int64_t glims_nslots(const glims_ctx* c) { return c ? c->pat.n_slots : 0; }
+void* glims_state_dev(glims_ctx* c) { return c ? c->x : nullptr; }
+void* glims_stream(glims_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int64_t glims_launch_count(const glims_ctx* c) { return c ? c->launches : 0; }
+
+int glims_step(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, glims_step_stats* stats) {
+    API_BEGIN
+    if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_step before glims_set_materials");
+    glims_solver_opts od;
+    if (!o) { glims_default_opts(&od); o = &od; }
+    for (int s = 0; s < n_steps; ++s) {
+        newton_step(c, o, stats ? &stats[s] : nullptr);
+        // u_previous.assign(solution)  (simulation_base.py:312)
+        launch_copy(c, c->x, c->xprev, c->ndof);
+    }
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_assemble(glims_ctx* c, int32_t what, int32_t kernel, int32_t apply_bc) {
+    API_BEGIN
+    if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_assemble before glims_set_materials");
+    halo_exchange(c, c->x, c->nb);
+    launch_assemble(c, what, kernel);
+    if (apply_bc) {
+        if (what & GLIMS_ASM_RESIDUAL) launch_bc_residual(c, c->F, c->x);
+        if (what & GLIMS_ASM_JACOBIAN) launch_bc_matrix(c, what & GLIMS_ASM_JACOBIAN, apply_bc == 2);
+    }
+    if (what & GLIMS_ASM_KCONST) {
+        c->kconst_valid = (apply_bc == 2);
+        if (c->kconst_valid) launch_diag_inverse(c, 1);
+        if (c->amg) amg_free(c);
+    }
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_get_residual(glims_ctx* c, double* F) { return F ? copy_vec(c, c ? c->F : nullptr, F, nullptr) : GLIMS_ERR_ARG; }
+
+int glims_export_pattern(glims_ctx* c, int64_t* rowptr, int32_t* colidx) {
+    API_BEGIN
+    auto& p = c->pat;
+    std::vector<i64> so(p.n_slices + 1);
+    std::vector<int> col(p.n_slots);
+    GL_CUDA(cudaMemcpy(rowptr, p.rowptr, sizeof(i64) * (p.n_rows + 1), cudaMemcpyDeviceToHost));
+    GL_CUDA(cudaMemcpy(so.data(), p.slice_off, sizeof(i64) * (p.n_slices + 1), cudaMemcpyDeviceToHost));
+    GL_CUDA(cudaMemcpy(col.data(), p.col, sizeof(int) * p.n_slots, cudaMemcpyDeviceToHost));
+    for (i64 r = 0; r < p.n_rows; ++r)
+        for (i64 t = rowptr[r]; t < rowptr[r + 1]; ++t)
+            colidx[t] = col[so[r >> 5] + (t - rowptr[r]) * 32 + (r & 31)];
+    API_END
+}
+
+int glims_export_values(glims_ctx* c, double* Kuu, double* Kuc, double* Kcc) {
+    API_BEGIN
+    i64 nz = c->pat.nnzb; int D = c->dim;
+    double *a = ws(c, "exp_uu", nz * D * D), *b = ws(c, "exp_uc", nz * D), *d = ws(c, "exp_cc", nz);
+    launch_export_values(c, a, b, d);
+    if (Kuu) GL_CUDA(cudaMemcpyAsync(Kuu, a, sizeof(double) * nz * D * D, cudaMemcpyDeviceToHost, c->stream));
+    if (Kuc) GL_CUDA(cudaMemcpyAsync(Kuc, b, sizeof(double) * nz * D, cudaMemcpyDeviceToHost, c->stream));
+    if (Kcc) GL_CUDA(cudaMemcpyAsync(Kcc, d, sizeof(double) * nz, cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_spmv(glims_ctx* c, int32_t which, const double* x, double* y) {
+    API_BEGIN
+    int bs = which == 0 ? c->nb : which == 1 ? c->dim : 1;
+    if (which < 0 || which > 2 || !x || !y) throw GlError(GLIMS_ERR_ARG, "glims_spmv: bad arguments");
+    double *dx = ws(c, "spmv_x", c->n_v * bs), *dy = ws(c, "spmv_y", c->n_v * bs);
+    GL_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * c->n_v * bs, cudaMemcpyHostToDevice, c->stream));
+    halo_exchange(c, dx, bs);
+    launch_spmv(c, which, dx, dy);
+    GL_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * c->pat.n_rows * bs, cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t reps, int32_t do_flush, float* ms_avg) {
+    API_BEGIN
+    if (!c->have_mat || reps <= 0 || !ms_avg) throw GlError(GLIMS_ERR_ARG, "glims_time_kernel: bad arguments/state");
+    int bs = kernel == 1 ? c->nb : kernel == 2 ? c->dim : 1;
+    double *dx = ws(c, "tk_x", c->ndof), *dy = ws(c, "tk_y", c->ndof);
+    if (kernel >= 1 && kernel <= 3) launch_copy(c, c->x, dx, c->n_v * bs);
+    auto run = [&]() {
+        switch (kernel) {
+            case 0: launch_assemble(c, GLIMS_ASM_ALL, variant); break;
+            case 1: launch_spmv(c, 0, dx, dy); break;
+            case 2: launch_spmv(c, 1, dx, dy); break;
+            case 3: launch_spmv(c, 2, dx, dy); break;
+            case 4: launch_assemble(c, GLIMS_ASM_RESIDUAL, variant); break;
+            default: throw GlError(GLIMS_ERR_ARG, "glims_time_kernel: unknown kernel");
+        }
+    };
+    for (int w = 0; w < 3; ++w) run();
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float tot = 0;
+    for (int r = 0; r < reps; ++r) {
+        if (do_flush) flush_l2(c);
+        cudaEventRecord(a, c->stream);
+        run();
+        cudaEventRecord(b, c->stream);
+        GL_CUDA(cudaEventSynchronize(b));
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        tot += ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_avg = tot / reps;
+    if (kernel == 0) c->kconst_valid = false;   // raw matrices: no Dirichlet elimination applied
+    API_END
+}
+
+}  // extern "C"

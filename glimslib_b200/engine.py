@@ -1,0 +1,201 @@
+"""Python handle on one ``glims_ctx`` (one GPU): the object the drop-in simulation classes drive.
+
+It owns no numerics -- every method is a C-ABI call into the CUDA library; numpy arrays are only
+the host buffers the ABI reads from / writes to.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class SolverNotConverged(RuntimeError):
+    """Raised when the device Newton/Krylov solve fails -- ``simulation_base.py:301-305`` catches it."""
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, coords, cells, cell_mat, device=0, n_owned=-1):
+        self._lib = N.load()
+        coords = N.f64(coords)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        cell_mat = np.ascontiguousarray(cell_mat, dtype=np.int32)
+        if coords.ndim != 2 or coords.shape[1] not in (2, 3):
+            raise ValueError("coords must be (n_vertices, 2|3)")
+        if cells.ndim != 2 or cells.shape[1] != coords.shape[1] + 1 or len(cell_mat) != len(cells):
+            raise ValueError("cells must be (n_cells, dim+1) with one material index per cell")
+        if cells.min() < 0 or cells.max() >= len(coords):
+            raise ValueError("cell vertex index out of range")
+        self.dim = coords.shape[1]
+        self.nb = self.dim + 1
+        self.n_vertices = len(coords)
+        self.n_cells = len(cells)
+        self.n_owned = self.n_vertices if n_owned < 0 else int(n_owned)
+        self._h = C.c_void_p()
+        rc = self._lib.glims_create(C.byref(self._h), self.dim, self.n_vertices, N.as_dp(coords), self.n_cells,
+                                    N.as_ip(cells), N.as_ip(cell_mat), int(n_owned), int(device))
+        if rc != 0:
+            msg = self._lib.glims_last_error(self._h).decode() if self._h else "glims_create failed"
+            raise EngineError("glims_create: rc=%d %s" % (rc, msg))
+        self.ndof = int(self._lib.glims_ndof(self._h))
+        self.opts = N.SolverOpts()
+        self._lib.glims_default_opts(C.byref(self.opts))
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc == 0:
+            return
+        msg = self._lib.glims_last_error(self._h).decode()
+        if rc == N.ERR_NOT_CONVERGED:
+            raise SolverNotConverged("%s: %s" % (what, msg))
+        raise EngineError("%s: rc=%d %s" % (what, rc, msg))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.glims_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- problem definition -------------------------------------------------------------------
+    def set_materials(self, table):
+        t = N.f64(table)
+        if t.ndim != 2 or t.shape[1] != 5:
+            raise ValueError("material table must be (n_mat, 5): mu, lambda, D, rho, gamma")
+        self._check(self._lib.glims_set_materials(self._h, len(t), N.as_dp(t)), "set_materials")
+
+    def set_dt(self, dt):
+        self._check(self._lib.glims_set_dt(self._h, float(dt)), "set_dt")
+
+    def set_dirichlet(self, dofs, vals):
+        d = np.ascontiguousarray(dofs, dtype=np.int64)
+        v = N.f64(vals)
+        if len(d) != len(v):
+            raise ValueError("dofs and vals differ in length")
+        self._check(self._lib.glims_set_dirichlet(self._h, len(d), N.as_lp(d), N.as_dp(v)), "set_dirichlet")
+
+    def set_load(self, f_ext):
+        if f_ext is None:
+            self._check(self._lib.glims_set_load(self._h, None), "set_load")
+        else:
+            f = N.f64(f_ext)
+            assert f.size == self.ndof
+            self._check(self._lib.glims_set_load(self._h, N.as_dp(f)), "set_load")
+
+    # -- state --------------------------------------------------------------------------------
+    def _vec(self, fn, name, x=None):
+        if x is None:
+            out = np.empty(self.ndof)
+            self._check(fn(self._h, N.as_dp(out)), name)
+            return out
+        a = N.f64(x).ravel()
+        assert a.size == self.ndof, "%s: expected %d values" % (name, self.ndof)
+        self._check(fn(self._h, N.as_dp(a)), name)
+
+    def set_state(self, x):
+        self._vec(self._lib.glims_set_state, "set_state", x)
+
+    def get_state(self):
+        return self._vec(self._lib.glims_get_state, "get_state")
+
+    def set_prev(self, x):
+        self._vec(self._lib.glims_set_prev, "set_prev", x)
+
+    def get_prev(self):
+        return self._vec(self._lib.glims_get_prev, "get_prev")
+
+    # -- hot path -----------------------------------------------------------------------------
+    def step(self, n_steps=1, **opts):
+        """``n_steps`` x (Newton-Krylov solve + ``u_previous.assign``). Returns per-step stats dicts."""
+        for k, v in opts.items():
+            setattr(self.opts, k, v)
+        stats = (N.StepStats * n_steps)()
+        rc = self._lib.glims_step(self._h, n_steps, C.byref(self.opts), stats)
+        out = [s.as_dict() for s in stats]
+        self.last_stats = out
+        self._check(rc, "step")
+        return out
+
+    # -- building blocks ----------------------------------------------------------------------
+    def assemble(self, what=N.ASM_ALL, kernel=N.ASMK_ATOMIC, apply_bc=0):
+        self._check(self._lib.glims_assemble(self._h, what, kernel, apply_bc), "assemble")
+
+    def residual(self):
+        return self._vec(self._lib.glims_get_residual, "get_residual")
+
+    def export_blocks(self):
+        """(rowptr, colidx, Kuu[nnzb,d,d], Kuc[nnzb,d], Kcc[nnzb]) in CSR block order."""
+        nnzb = int(self._lib.glims_nnzb(self._h))
+        d = self.dim
+        rowptr = np.empty(self.n_owned + 1, dtype=np.int64)
+        col = np.empty(nnzb, dtype=np.int32)
+        self._check(self._lib.glims_export_pattern(self._h, N.as_lp(rowptr), N.as_ip(col)), "export_pattern")
+        Kuu, Kuc, Kcc = np.empty((nnzb, d, d)), np.empty((nnzb, d)), np.empty(nnzb)
+        self._check(self._lib.glims_export_values(self._h, N.as_dp(Kuu), N.as_dp(Kuc), N.as_dp(Kcc)), "export_values")
+        return rowptr, col, Kuu, Kuc, Kcc
+
+    def export_jacobian(self):
+        """Monolithic Jacobian as a scipy CSR matrix in vertex-blocked dof order."""
+        import scipy.sparse as sp
+        rowptr, col, Kuu, Kuc, Kcc = self.export_blocks()
+        d, nb = self.dim, self.nb
+        blocks = np.zeros((len(col), nb, nb))
+        blocks[:, :d, :d] = Kuu
+        blocks[:, :d, d] = Kuc
+        blocks[:, d, d] = Kcc
+        J = sp.bsr_matrix((blocks, col, rowptr), shape=(self.n_owned * nb, self.n_vertices * nb))
+        return J.tocsr()
+
+    def spmv(self, which, x):
+        bs = {0: self.nb, 1: self.dim, 2: 1}[which]
+        a = N.f64(x).ravel()
+        assert a.size == self.n_vertices * bs
+        y = np.empty(self.n_owned * bs)
+        self._check(self._lib.glims_spmv(self._h, which, N.as_dp(a), N.as_dp(y)), "spmv")
+        return y
+
+    def time_kernel(self, kernel, variant=0, reps=10, flush_l2=True):
+        ms = C.c_float()
+        self._check(self._lib.glims_time_kernel(self._h, kernel, variant, reps, int(flush_l2), C.byref(ms)), "time_kernel")
+        return float(ms.value)
+
+    @property
+    def nnzb(self):
+        return int(self._lib.glims_nnzb(self._h))
+
+    @property
+    def nslots(self):
+        return int(self._lib.glims_nslots(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.glims_launch_count(self._h))
+
+    # -- multi-GPU ----------------------------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_char * 128)()
+        rc = N.load().glims_nccl_unique_id(buf)
+        if rc != 0:
+            raise EngineError("ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self._lib.glims_comm_init(self._h, n_ranks, rank, buf), "comm_init")
+
+    def set_halo(self, peers, send_ptr, send_idx, recv_ptr):
+        peers = np.ascontiguousarray(peers, dtype=np.int32)
+        send_ptr = np.ascontiguousarray(send_ptr, dtype=np.int64)
+        send_idx = np.ascontiguousarray(send_idx, dtype=np.int32)
+        recv_ptr = np.ascontiguousarray(recv_ptr, dtype=np.int64)
+        self._check(self._lib.glims_set_halo(self._h, len(peers), N.as_ip(peers), N.as_lp(send_ptr),
+                                             N.as_ip(send_idx), N.as_lp(recv_ptr)), "set_halo")

@@ -1,0 +1,208 @@
+"""GPU parity tests: every number the CUDA path produces is compared with the CPU oracle on the
+same seeded inputs, through the C ABI (ctypes).  FP64 path; tolerances are stated per test."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import fem, meshes, solver as osolver
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(*a, **k):
+    from glimslib_b200.engine import Engine
+    return Engine(*a, **k)
+
+
+def small_problem(d, seed=0, n=4, jitter=0.15, with_bc=True):
+    rng = np.random.default_rng(seed)
+    if d == 2:
+        coords, cells = meshes.rectangle_mesh((0, 0), (1.0, 1.3), n + 1, n)
+    else:
+        coords, cells = meshes.box_mesh((0, 0, 0), (1, 1.2, 0.8), n, n - 1, n)
+    h = 1.0 / (n + 1)
+    bv = meshes.boundary_vertices(cells, len(coords))
+    interior = np.ones(len(coords), bool)
+    interior[bv] = False
+    coords = coords.copy()
+    coords[interior] += jitter * h * (rng.random((interior.sum(), d)) - 0.5)
+    cm = rng.integers(0, 3, len(cells)).astype(np.int32)
+    mats = fem.Materials.from_E_nu([3e-3, 1e-3, 2e-3], [0.45, 0.3, 0.49], [0.1, 0.02, 0.0], [0.2, 0.05, 0.0],
+                                   [0.15, 0.0, 0.3])
+    nb = d + 1
+    if with_bc:
+        dofs = (bv[:, None] * nb + np.arange(d)[None, :]).ravel()
+        vals = 0.01 * rng.standard_normal(len(dofs))
+        # a few concentration Dirichlet dofs too (sub-space 1 BCs are legal, helper_classes.py:673-723)
+        cd = bv[::7] * nb + d
+        dofs = np.concatenate([dofs, cd])
+        vals = np.concatenate([vals, 0.3 * np.ones(len(cd))])
+    else:
+        dofs, vals = np.zeros(0, np.int64), np.zeros(0)
+    prob = fem.Problem(coords, cells, cm, mats, dt=0.7, bc_dofs=dofs.astype(np.int64), bc_vals=vals)
+    prob.f_ext = 1e-3 * rng.standard_normal(prob.ndof)
+    return prob, rng
+
+
+def make_engine(prob):
+    eng = _engine(prob.coords, prob.cells, prob.cell_mat)
+    eng.set_materials(prob.mats.table())
+    eng.set_dt(prob.dt)
+    eng.set_dirichlet(prob.bc_dofs, prob.bc_vals)
+    eng.set_load(prob.f_ext)
+    return eng
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_assembly_matches_oracle(d, kernel):
+    """K1/K2: residual and Jacobian values, raw and with DOLFIN-style Dirichlet rows; <= 1e-13 relative."""
+    prob, rng = small_problem(d)
+    x, xp = rng.standard_normal(prob.ndof), rng.standard_normal(prob.ndof)
+    eng = make_engine(prob)
+    eng.set_state(x)
+    eng.set_prev(xp)
+    F0, J0 = fem.assemble(prob, x, xp)
+    eng.assemble(kernel=kernel, apply_bc=0)
+    assert relerr(eng.residual(), F0) < 1e-13
+    J = eng.export_jacobian()
+    assert abs(J - J0).max() / abs(J0).max() < 1e-13
+    F1, J1 = fem.apply_dirichlet(prob, F0, J0, x)
+    eng.assemble(kernel=kernel, apply_bc=1)
+    assert relerr(eng.residual(), F1) < 1e-13
+    J = eng.export_jacobian()
+    assert abs(J - J1).max() / abs(J1).max() < 1e-13
+    # rows + columns (symmetric elimination) keeps the symmetric blocks symmetric
+    eng.assemble(kernel=kernel, apply_bc=2)
+    J = eng.export_jacobian()
+    nb = d + 1
+    keep = np.ones(prob.ndof)
+    keep[prob.bc_dofs] = 0
+    J2 = (sp.diags(keep) @ J0 @ sp.diags(keep) + sp.diags(1 - keep)).tocsr()
+    assert abs(J - J2).max() / abs(J2).max() < 1e-13
+    eng.close()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_atomic_and_gather_kernels_agree(d):
+    prob, rng = small_problem(d, seed=3, n=6)
+    eng = make_engine(prob)
+    eng.set_state(rng.standard_normal(prob.ndof))
+    eng.assemble(what=6, kernel=0)
+    a = eng.export_blocks()
+    eng.assemble(what=6, kernel=1)
+    b = eng.export_blocks()
+    for p, q in zip(a[2:], b[2:]):
+        assert relerr(p, q) < 1e-13
+    eng.close()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_spmv_matches_oracle(d):
+    """K4: SELL-32 SpMV of the monolithic Jacobian and of each block; <= 1e-13 relative."""
+    prob, rng = small_problem(d, seed=1, n=5)
+    x = rng.standard_normal(prob.ndof)
+    eng = make_engine(prob)
+    eng.set_state(x)
+    eng.set_prev(x)
+    eng.assemble(apply_bc=1)
+    _, J = fem.assemble(prob, x, x)
+    _, J = fem.apply_dirichlet(prob, np.zeros(prob.ndof), J, x)
+    v = rng.standard_normal(prob.ndof)
+    assert relerr(eng.spmv(0, v), J @ v) < 1e-13
+    nb = d + 1
+    iu = (np.arange(prob.ndof) % nb) < d
+    vu, vc = rng.standard_normal(iu.sum()), rng.standard_normal((~iu).sum())
+    assert relerr(eng.spmv(1, vu), J[iu][:, iu] @ vu) < 1e-13
+    assert relerr(eng.spmv(2, vc), J[~iu][:, ~iu] @ vc) < 1e-13
+    eng.close()
+
+
+def c1_problem(nx=50):
+    """test_case_simulation_tumor_growth_2D_subdomains.py:34-89 (config C1)."""
+    coords, cells = meshes.rectangle_mesh((-5, -5), (5, 5), nx, nx)
+    lab_v = np.where(coords[:, 0] >= 0, 1.0, 2.0)
+    lab = lab_v[cells].mean(axis=1).astype(int)          # helper_classes.py:441-442 on the DG1 label function
+    mats = fem.Materials.from_E_nu([1e-3, 1e-3], [0.4, 0.1], [0.1, 0.0], [0.1, 0.0], [0.2, 0.0])
+    bv = meshes.boundary_vertices(cells, len(coords))
+    dofs = np.sort(np.concatenate([bv * 3, bv * 3 + 1]))
+    prob = fem.Problem(coords, cells, (lab - 1).astype(np.int32), mats, dt=1.0, bc_dofs=dofs,
+                       bc_vals=np.zeros(len(dofs)))
+    x0 = np.zeros(prob.ndof)
+    r = np.hypot(coords[:, 0] - 2.5, coords[:, 1] - 2.5)
+    x0[2::3] = (r < 0.4).astype(float)
+    return prob, x0
+
+
+@pytest.mark.parametrize("mode", ["block_tri_jacobi", "block_tri_amg", "block_tri_nolag", "mono_gmres"])
+def test_c1_time_loop_matches_oracle(mode):
+    """Config C1, 10 backward-Euler steps: each step's field within 1e-8 relative L2 of the oracle
+    (oracle: Newton + sparse LU to rtol 1e-12).  The device solve runs SNES rtol 1e-10 / KSP rtol 1e-12."""
+    prob, x0 = c1_problem()
+    recs, _ = osolver.run(prob, x0, 10, linear="lu", rtol=1e-12, atol=1e-14)
+    eng = make_engine(prob)
+    eng.set_prev(x0)
+    eng.set_state(np.zeros(prob.ndof))
+    kw = dict(snes_rtol=1e-10, snes_atol=1e-13, ksp_rtol=1e-12)
+    if mode == "mono_gmres":
+        kw.update(solver=1)
+    elif mode == "block_tri_jacobi":
+        kw.update(solver=0, pc=0)
+    elif mode == "block_tri_amg":
+        kw.update(solver=0, pc=1)
+    else:
+        kw.update(solver=0, pc=0, lag_mechanics=0)
+    nb = 3
+    for k in range(1, 11):
+        st = eng.step(1, **kw)[0]
+        assert st["converged"] == 1
+        x = eng.get_state()
+        ref = recs[k][2]
+        for comp, name in ((slice(2, None, nb), "concentration"),):
+            e = np.linalg.norm(x[comp] - ref[comp]) / np.linalg.norm(ref[comp])
+            assert e < 1e-8, (k, name, e)
+        u = x.reshape(-1, nb)[:, :2]
+        ur = ref.reshape(-1, nb)[:, :2]
+        e = np.linalg.norm(u - ur) / np.linalg.norm(ur)
+        assert e < 1e-8, (k, "displacement", e)
+    eng.close()
+
+
+def test_3d_coupled_steps_match_oracle():
+    """3D two-tissue coupled box (config C3 shrunk to 8^3): 3 steps within 1e-8 relative L2."""
+    coords, cells = meshes.box_mesh((0, 0, 0), (1, 1, 1), 8, 8, 8)
+    cm = (coords[cells].mean(axis=1)[:, 0] >= 0.5).astype(np.int32)
+    mats = fem.Materials.from_E_nu([3e-3, 1e-3], [0.45, 0.45], [0.002, 0.0], [0.05, 0.0], [0.1, 0.0])
+    bv = meshes.boundary_vertices(cells, len(coords))
+    dofs = np.sort((bv[:, None] * 4 + np.arange(3)[None, :]).ravel())
+    prob = fem.Problem(coords, cells, cm, mats, dt=1.0, bc_dofs=dofs, bc_vals=np.zeros(len(dofs)))
+    x0 = np.zeros(prob.ndof)
+    x0[3::4] = np.exp(-40 * ((coords - np.array([0.35, 0.5, 0.5])) ** 2).sum(axis=1))
+    recs, _ = osolver.run(prob, x0, 3, linear="lu", rtol=1e-12, atol=1e-15)
+    eng = make_engine(prob)
+    eng.set_prev(x0)
+    eng.set_state(np.zeros(prob.ndof))
+    for k in range(1, 4):
+        st = eng.step(1, snes_rtol=1e-10, snes_atol=1e-14, ksp_rtol=1e-12)[0]
+        assert st["converged"] == 1
+        x = eng.get_state().reshape(-1, 4)
+        ref = recs[k][2].reshape(-1, 4)
+        assert np.linalg.norm(x[:, 3] - ref[:, 3]) / np.linalg.norm(ref[:, 3]) < 1e-8
+        assert np.linalg.norm(x[:, :3] - ref[:, :3]) / np.linalg.norm(ref[:, :3]) < 1e-8
+    eng.close()
+
+
+def test_not_converged_is_reported():
+    """GLIMS_ERR_NOT_CONVERGED surfaces as an exception (simulation_base.py:301-305 catches it)."""
+    from glimslib_b200.engine import SolverNotConverged
+    prob, x0 = c1_problem(nx=10)
+    eng = make_engine(prob)
+    eng.set_prev(x0)
+    eng.set_state(np.zeros(prob.ndof))
+    with pytest.raises(SolverNotConverged):
+        eng.step(1, max_newton=1, snes_rtol=1e-14, snes_atol=1e-300)
+    eng.close()
