@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Headline benchmark: time steps per second of the mechanically-coupled reaction-diffusion model on the
+3D 10M-tet brain-like ellipsoid (BASELINE.json metric), plus the HBM
+roofline of the dominant kernels and a CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # one JSON line
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference path
+
+A "step" is one backward-Euler step = one `solver.solve()` of the reference (simulation_base.py:302):
+Newton-Krylov on the coupled system until the monolithic residual meets SNES rtol 1e-9 / atol 1e-10.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "timesteps/sec, 3D 10M-tet coupled RD-mechanics (config C4)"
+UNIT = "timesteps/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.split(",") for l in open(self.f.name).read().strip().splitlines() if l.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows]
+        out["sm_mhz"] = float(np.median(sm))
+        out["sm_max_mhz"] = float(rows[0][2])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nm in enumerate(names):
+            if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows):
+                out["reasons"].append(nm)
+        out["samples"] = len(rows)
+        return out
+
+
+def oracle_problem(w):
+    from oracle import fem
+    t = w["table"]
+    return fem.Problem(w["mesh"].coords, w["mesh"].cells, w["cell_mat"],
+                       fem.Materials(t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4]), w["dt"],
+                       bc_dofs=w["bc_dofs"], bc_vals=w["bc_vals"])
+
+
+def cpu_baseline(full_cells, steps=1, n_sample=24):
+    """Oracle (numpy/scipy restatement of the reference path; Newton + GMRES(30)/ILU like PETSc's defaults)
+    on a bounded sample: the same C4 configuration at a coarser voxel grid.  Throughput is scaled
+    linearly in the cell count to the full workload (optimistic for the CPU: its solve is superlinear)."""
+    from glimslib_b200 import workloads as W
+    from oracle import fem, solver as osolver
+    w = W.c4_ellipsoid(n_sample)
+    prob = oracle_problem(w)
+    geom = fem.geometry(prob.coords, prob.cells)
+    x_prev = w["x0"].copy()
+    x = np.zeros_like(x_prev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x, _ = osolver.newton(prob, x, x_prev, linear="gmres_ilu", geom=geom)
+        x_prev = x.copy()
+    dt = time.perf_counter() - t0
+    nc = w["mesh"].num_cells()
+    sps_sample = steps / dt
+    return {"value": sps_sample * nc / full_cells, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "C4 at voxel grid n=%d (%d tets), %d step(s) in %.1f s = %.4f steps/s on the sample; "
+                      "scaled x(%d/%d) to the full mesh; scipy GMRES(30)+spilu, single-threaded; "
+                      "restatement, not FEniCS" % (n_sample, nc, steps, dt, sps_sample, nc, full_cells)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port timed on host cores (FEniCS itself is not installable here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    full_cells = 10185024
+    K, Wm = args.steps, args.warmup
+    # bounded: each step is one backward-Euler step on the n=24 sample (~15 s); cap the run at a few minutes
+    K = max(1, min(K, 6))
+    Wm = min(Wm, 1)
+    from glimslib_b200 import workloads as W
+    from oracle import fem, solver as osolver
+    w = W.c4_ellipsoid(24)
+    prob = oracle_problem(w)
+    geom = fem.geometry(prob.coords, prob.cells)
+    x_prev = w["x0"].copy()
+    x = np.zeros_like(x_prev)
+    for _ in range(Wm):
+        x, _ = osolver.newton(prob, x, x_prev, linear="gmres_ilu", geom=geom)
+        x_prev = x.copy()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        x, _ = osolver.newton(prob, x, x_prev, linear="gmres_ilu", geom=geom)
+        x_prev = x.copy()
+    dt = time.perf_counter() - t0
+    nc = w["mesh"].num_cells()
+    val = K / dt * nc / full_cells
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": Wm, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 3D voxel ellipsoid n=148, 10185024 tets, three tissues, coupled "
+                                   "(timed on a bounded sample, see cpu_baseline.sample)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "C4 at n=24 (%d tets): %d steps in %.1f s, scaled x(%d/%d) to the full mesh; "
+                                       "oracle port (scipy GMRES(30)+ILU), FEniCS not installable offline"
+                                       % (nc, K, dt, nc, full_cells)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def algorithmic_bytes(d, n_v, n_c, nnzb):
+    nb = d + 1
+    return {
+        "spmv_kuu": (8 * d * d + 4) * nnzb + 16 * d * n_v,
+        "spmv_mono": (8 * (d * d + d + 1) + 4) * nnzb + 16 * nb * n_v,
+        "spmv_kcc": 12 * nnzb + 16 * n_v,
+        "assembly_full": n_c * (4 * nb + 8 * d * nb + 4) + 8 * (d * d + d + 1) * nnzb + 3 * 8 * nb * n_v,
+        "residual": n_c * (4 * nb + 8 * d * nb + 4) + 3 * 8 * nb * n_v,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--n", type=int, default=148, help="voxel grid of the C4 ellipsoid (148 -> 10.19M tets)")
+    ap.add_argument("--pc", default="amg", choices=["amg", "jacobi"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from glimslib_b200 import _native as N
+    from glimslib_b200 import workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    W_steps = max(args.warmup, 3)
+    K = args.steps
+
+    w = W.c4_ellipsoid(args.n)
+    d = 3
+    if world > 1:
+        from glimslib_b200 import distributed as D
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        eng, part = D.build_distributed_engine(w, rank, world, local_rank, dist)
+    else:
+        eng = W.build_engine(w, device=local_rank)
+        part = None
+    opts = dict(pc=N.PC_AMG if args.pc == "amg" else N.PC_JACOBI)
+
+    def local_vec(x):
+        return x if part is None else part.to_local(x)
+
+    x0 = local_vec(w["x0"])
+    eng.set_prev(x0)
+    eng.set_state(np.zeros_like(x0))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: state already in HBM ------------------------------------------
+    eng.step(W_steps, **opts)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    stats = eng.step(K, **opts)
+    barrier()
+    t1 = time.perf_counter()
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    elapsed = t1 - t0
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt.item())
+    dev_ms = float(np.mean([s["ms_total"] for s in stats]))
+
+    # ---- end to end through the host-buffer API: H2D of the step inputs, D2H of the result -----
+    ndof = eng.ndof
+    pin_in = torch.empty(ndof, dtype=torch.float64).pin_memory().numpy()
+    pin_out = torch.empty(ndof, dtype=torch.float64).pin_memory().numpy()
+    pin_in[:] = eng.get_state()
+    import ctypes
+    lib = eng._lib
+    K2 = max(3, min(K, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K2):
+        rc = lib.glims_set_prev(eng._h, N.as_dp(pin_in))          # H2D: u_previous
+        rc |= lib.glims_set_state(eng._h, N.as_dp(pin_in))        # H2D: Newton start = last solution
+        assert rc == 0
+        eng.step(1, **opts)
+        assert lib.glims_get_state(eng._h, N.as_dp(pin_out)) == 0   # D2H: the step's solution
+        pin_in[:] = pin_out
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([e2e_elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_elapsed = float(tt.item())
+    e2e = {"value": K2 / e2e_elapsed, "unit": UNIT, "h2d_bytes_per_step": 2 * ndof * 8 * world,
+           "d2h_bytes_per_step": ndof * 8 * world, "steps": K2}
+
+    # ---- roofline of the dominant kernels (CUDA events on the library's stream, L2 flushed) ----
+    roof, kernels = None, {}
+    if rank == 0 and not args.no_roofline:
+        peak, peak_src = peaks()
+        n_v, n_c, nnzb = eng.n_owned, eng.n_cells, eng.nnzb
+        ab = algorithmic_bytes(d, n_v, n_c, nnzb)
+        for name, kid, variant, key in (("spmv_kuu", 2, 0, "spmv_kuu"), ("spmv_mono", 1, 0, "spmv_mono"),
+                                        ("spmv_kcc", 3, 0, "spmv_kcc"),
+                                        ("assembly_full_gather", 0, 1, "assembly_full"),
+                                        ("assembly_full_atomic", 0, 0, "assembly_full"),
+                                        ("residual", 4, 0, "residual")):
+            ms = eng.time_kernel(kid, variant, reps=10, flush_l2=True)
+            gbs = ab[key] / ms / 1e6
+            kernels[name] = {"ms": ms, "algorithmic_bytes": ab[key], "achieved_gbs": gbs, "frac": gbs / peak}
+        k = kernels["spmv_kuu"]
+        roof = {"bound": "hbm", "kernel": "k_spmv_block<3,3> (K_uu SELL-32 SpMV inside PCG)", "achieved": k["achieved_gbs"],
+                "peak": peak, "unit": "GB/s", "frac": k["frac"], "traffic": None, "peak_source": peak_src}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(w["mesh"].num_cells())
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": K / elapsed, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_steps,
+            "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "n_tets": int(w["mesh"].num_cells()),
+                       "n_vertices": int(w["mesh"].num_vertices()), "n_dofs": int(w["mesh"].num_vertices() * 4),
+                       "nnz_blocks": int(eng.nnzb), "dt": w["dt"], "solver": "block-triangular Newton-PCG, pc=%s" % args.pc,
+                       "tolerances": "SNES rtol 1e-9 atol 1e-10 (monolithic |F|), KSP rtol 1e-10",
+                       "timing": "inputs larger than L2 (matrix 1.9 GB, vectors 42-56 MB); wall clock between "
+                                 "device syncs, max over ranks",
+                       "device_ms_per_step": dev_ms,
+                       "newton_its_per_step": float(np.mean([s["newton_its"] for s in stats])),
+                       "krylov_its_u_per_step": float(np.mean([s["krylov_its_u"] for s in stats])),
+                       "krylov_its_c_per_step": float(np.mean([s["krylov_its_c"] for s in stats])),
+                       "ms_assembly_per_step": float(np.mean([s["ms_assembly"] for s in stats])),
+                       "ms_krylov_per_step": float(np.mean([s["ms_krylov"] for s in stats])),
+                       "final_fnorm": stats[-1]["fnorm"], "parallelism": "vertex partition x%d" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -199,7 +199,7 @@ def test_3d_coupled_steps_match_oracle():
 def test_not_converged_is_reported():
     """GLIMS_ERR_NOT_CONVERGED surfaces as an exception (simulation_base.py:301-305 catches it)."""
     from glimslib_b200.engine import SolverNotConverged
-    prob, x0 = c1_problem(nx=10)
+    prob, x0 = c1_problem(nx=20)
     eng = make_engine(prob)
     eng.set_prev(x0)
     eng.set_state(np.zeros(prob.ndof))
