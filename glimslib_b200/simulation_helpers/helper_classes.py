@@ -1,0 +1,773 @@
+"""Helper classes of the drop-in API, re-implemented for the B200 backend.
+
+Same public names, arguments and error behaviour as ``glimslib/simulation_helpers/helper_classes.py`` for
+everything on or next to the hot path: ``FunctionSpace``/``SubSpaces``,
+``SubDomains``, ``BoundaryConditions``, ``Parameters``, ``Results`` and the ``TimeSeries*`` containers.  The
+bodies are new: label assignment, interface detection and Dirichlet/Neumann set construction are vectorised
+numpy over the mesh arrays (the reference loops over cells/facets in Python, helper_classes.py:441-442,
+479-491), and per-tissue parameters become rows of the material table staged to the GPU instead of
+``DiscontinuousScalar`` callbacks (helper_classes.py:47-58).  Plotting / post-processing (rows 9, 13) are
+out of scope: ``Plotting`` warns and skips.
+"""
+import itertools
+import logging
+import os
+import shutil
+
+import numpy as np
+
+from glimslib_b200 import fenics_local as fenics
+from glimslib_b200.simulation import config
+
+
+def _ensure_dir(path):
+    d = path if not os.path.splitext(path)[1] else os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+
+
+class Boundary(fenics.SubDomain):
+    def inside(self, x, on_boundary):
+        return on_boundary
+
+
+class DiscontinuousScalar:
+    """Per-subdomain scalar: ``values[label]`` per cell. Counterpart of helper_classes.py:47-58, keyed by label
+    id (the intended semantics; the reference indexes by dict position -- SURVEY.md quirk Q2)."""
+
+    def __init__(self, cell_function, value_by_label, name=None):
+        self.cell_function, self.value_by_label, self.name = cell_function, dict(value_by_label), name
+
+    def cell_values(self):
+        lab = np.asarray(self.cell_function.array())
+        out = np.zeros(len(lab))
+        for k, v in self.value_by_label.items():
+            out[lab == k] = float(v)
+        return out
+
+    def value_for_label(self, label):
+        return float(self.value_by_label.get(label, 0.0))
+
+
+# ==================================================================================================
+class SubSpaces:
+    """Book-keeping for functions living on several sub-spaces (helper_classes.py:66-232)."""
+
+    def __init__(self, names=None):
+        self.logger = logging.getLogger(__name__)
+        self.names = dict(names or {})
+        self.n = len(self.names)
+        self._store = {}
+
+    def get_subspace_names(self): return self.names.values()
+    def get_subspace_name(self, subspace_id): return self.names.get(subspace_id)
+    def get_subspace_ids(self): return self.names.keys()
+
+    def get_subspace_id(self, subspace_name):
+        for k, v in self.names.items():
+            if v == subspace_name:
+                return k
+        self.logger.warning("Functionspace does not have '%s' subspace." % subspace_name)
+        return None
+
+    def _set(self, name, content, replace=False):
+        if not isinstance(content, (list, dict)):
+            self.logger.error("Expect either list or dictionary")
+            return
+        if len(content) != self.n:
+            self.logger.error("Expect content with %i items, but this has %i items." % (self.n, len(content)))
+            return
+        d = dict(enumerate(content)) if isinstance(content, list) else content
+        if name in self._store and not replace:
+            self.logger.warning("Attribute '%s' already exists ... do nothing." % name)
+            return
+        self._store[name] = d
+
+    def _get(self, name, subspace_id=None, subspace_name=None):
+        if subspace_id is None and subspace_name is None:
+            self.logger.error("No subspace or subspace name specified")
+            return None
+        if subspace_id is None:
+            subspace_id = self.get_subspace_id(subspace_name)
+        d = self._store.get(name)
+        if d is None:
+            self.logger.warning("Attribute '%s' does not exist." % name)
+            return None
+        if subspace_id not in d:
+            self.logger.warning("Attribute '%s' has no information for subspace '%s'" % (name, subspace_id))
+            return None
+        return d[subspace_id]
+
+    def get_element(self, subspace_id=None, subspace_name=None): return self._get("elements", subspace_id, subspace_name)
+    def get_inital_value_expression(self, subspace_id=None, subspace_name=None): return self._get("ivs", subspace_id, subspace_name)
+    def get_functionspace(self, subspace_id=None, subspace_name=None): return self._get("functionspaces", subspace_id, subspace_name)
+    def get_dirichlet_bcs(self, subspace_id=None, subspace_name=None): return self._get("bcs_dirichlet", subspace_id, subspace_name)
+    def get_von_neumann_bcs(self, subspace_id=None, subspace_name=None): return self._get("bcs_von_neumann", subspace_id, subspace_name)
+    def set_elements(self, content, replace=False): self._set("elements", content, replace)
+    def set_inital_value_expressions(self, content, replace=False): self._set("ivs", content, replace)
+    def set_functionspaces(self, content, replace=False): self._set("functionspaces", content, replace)
+
+    def _by_subspace(self, specs):
+        out = {sid: [] for sid in self.names}
+        for name, spec in specs.items():
+            sid = spec.get("subspace_id")
+            if sid in out:
+                spec["name"] = name
+                out[sid].append(spec)
+        return out
+
+    def set_dirichlet_bcs(self, content, replace=False): self._set("bcs_dirichlet", self._by_subspace(content), replace)
+    def set_von_neumann_bcs(self, content, replace=False): self._set("bcs_von_neumann", self._by_subspace(content), replace)
+
+    def project_over_subspace(self, function_expr, subspace_id=None, subspace_name=None, **kwargs):
+        if subspace_id is None and subspace_name is None:
+            self.logger.error("No subspace or subspace name specified")
+            return None
+        if subspace_id is None:
+            subspace_id = self.get_subspace_id(subspace_name)
+        try:
+            return fenics.project(function_expr, self.get_functionspace(subspace_id=subspace_id))
+        except Exception as e:       # same "warn and return None" contract as helper_classes.py:225-232
+            self.logger.warning("Cannot project functions over subspace %s: %s" % (subspace_id, e))
+            return None
+
+
+class FunctionSpace:
+    """Mixed space + per-sub-space collapsed spaces (helper_classes.py:234-383)."""
+
+    def __init__(self, mesh, projection_parameters=None):
+        self.logger = logging.getLogger(__name__)
+        self._mesh = mesh
+        self.dim_geo = mesh.geometric_dimension()
+        self._projection_parameters = dict(projection_parameters or {})
+
+    def init_function_space(self, element, name):
+        self.element = element
+        if isinstance(name, dict):
+            self.has_subspaces = True
+            self.subspaces = SubSpaces(name)
+            self.subspaces.set_elements(self.element.sub_elements())
+        else:
+            self.has_subspaces = False
+            self.name = name
+        self._setup_function_space()
+
+    def _setup_function_space(self):
+        self.logger.info("   - setting up global function space")
+        self.function_space = fenics.FunctionSpace(self._mesh, self.element)
+        if self.has_subspaces:
+            self.subspaces.set_functionspaces({sid: fenics.FunctionSpace(self._mesh, self.subspaces.get_element(subspace_id=sid))
+                                               for sid in self.subspaces.names})
+
+    def get_element(self, subspace_id=None, subspace_name=None):
+        if self.has_subspaces and not (subspace_id is None and subspace_name is None):
+            return self.subspaces.get_element(subspace_id=subspace_id, subspace_name=subspace_name)
+        return self.element
+
+    def get_functionspace(self, subspace_id=None, subspace_name=None):
+        if self.has_subspaces and not (subspace_id is None and subspace_name is None):
+            return self.subspaces.get_functionspace(subspace_id=subspace_id, subspace_name=subspace_name)
+        return self.function_space
+
+    def get_functionspace_orig_subspace(self, subspace_id=None, subspace_name=None):
+        if subspace_id is None and subspace_name is None:
+            self.logger.error("No subspace or subspace name specified")
+            return None
+        if subspace_id is None:
+            subspace_id = self.subspaces.get_subspace_id(subspace_name)
+        return self.function_space.sub(subspace_id)
+
+    def project_over_space(self, function_expr, subspace_id=None, subspace_name=None, **kwargs):
+        if not self.has_subspaces:
+            return fenics.project(function_expr, self.function_space)
+        if isinstance(function_expr, dict):
+            return self._project_combine_multiple_subspaces(function_expr, **kwargs)
+        if subspace_id is None and subspace_name is None:
+            return fenics.project(function_expr, self.function_space)
+        return self.subspaces.project_over_subspace(function_expr, subspace_id=subspace_id, subspace_name=subspace_name)
+
+    def _project_combine_multiple_subspaces(self, function_expr_subspace_dict, **kwargs):
+        U = fenics.Function(self.function_space)
+        for key, expr in function_expr_subspace_dict.items():
+            sid = self.subspaces.get_subspace_id(key) if isinstance(key, str) else key
+            f = self.project_over_space(expr, subspace_id=sid)
+            fenics.FunctionAssigner(self.function_space.sub(sid), self.subspaces.get_functionspace(subspace_id=sid)).assign(U.sub(sid), f)
+        return U
+
+    def split_function(self, function, subspace_id=None, subspace_name=None):
+        if not self.has_subspaces or (subspace_id is None and subspace_name is None):
+            return function
+        if subspace_id is None:
+            subspace_id = self.subspaces.get_subspace_id(subspace_name)
+        return fenics.split(function)[subspace_id]
+
+
+# ==================================================================================================
+class SubDomains:
+    """Cell labels, subdomain-interface facets, named boundaries, per-label coefficients
+    (helper_classes.py:385-615)."""
+
+    def __init__(self, mesh):
+        self.logger = logging.getLogger(__name__)
+        self._mesh = mesh
+        self.dim_geo = mesh.geometric_dimension()
+
+    def setup_subdomains(self, label_function=None, subdomains=None, replace=False):
+        if hasattr(self, "subdomains") and not replace:
+            self.logger.warning("'subdomains' already exists ... do nothing.")
+            return
+        if subdomains is not None:
+            self.subdomains = subdomains
+        elif label_function is not None:
+            self._setup_subdomains_from_labelmapfunction(label_function)
+        else:
+            self.subdomains = fenics.MeshFunction("size_t", self._mesh, self.dim_geo)
+            self.subdomains.set_all(0)
+
+    def _setup_subdomains_from_labelmapfunction(self, label_function):
+        """label(cell) = int(label_function(cell midpoint)) -- helper_classes.py:441-442, evaluated for all cells at once."""
+        self.label_function = label_function
+        sd = fenics.MeshFunction("size_t", self._mesh, self.dim_geo)
+        sd.array()[:] = label_function.cell_midpoint_values()[:, 0].astype(np.int64)   # int() truncation
+        self.subdomains = sd
+
+    def setup_boundaries(self, tissue_map=None, boundary_fct_dict=None):
+        if tissue_map is not None:
+            self._setup_boundaries_from_subdomains(tissue_map)
+        if boundary_fct_dict is not None:
+            self._setup_boundaries_from_functions(boundary_fct_dict)
+
+    def _setup_boundaries_from_subdomains(self, tissue_id_name_map):
+        """Facet ids for every unordered pair of tissues, named '<A>_<B>' in map order, plus 'no_boundary'
+        (helper_classes.py:457-501).  Pairs are matched as unordered sets (intended semantics, quirk Q3)."""
+        if not hasattr(self, "subdomains"):
+            self.logger.warning("Need subdomains to define boundaries. No subdomains defined.")
+            return
+        self.tissue_id_name_map = tissue_id_name_map
+        pairs = list(itertools.combinations(tissue_id_name_map.keys(), 2))
+        names = ["_".join(p) for p in itertools.combinations(tissue_id_name_map.values(), 2)]
+        id_dict = dict(zip(names, range(len(names))))
+        no_boundary = (max(id_dict.values()) + 1) if id_dict else 0
+        bnd = fenics.MeshFunction("size_t", self._mesh, self.dim_geo - 1)
+        _, _, fc = self._mesh.facets()
+        lab = np.asarray(self.subdomains.array())
+        l0 = lab[fc[:, 0]]
+        l1 = np.where(fc[:, 1] >= 0, lab[np.maximum(fc[:, 1], 0)], l0)
+        arr = bnd.array()
+        arr[:] = no_boundary          # facets inside one subdomain (and exterior facets): helper_classes.py:490-491
+        for (a, b), name in zip(pairs, names):
+            hit = ((l0 == a) & (l1 == b)) | ((l0 == b) & (l1 == a))
+            arr[hit] = id_dict[name]
+        id_dict["no_boundary"] = no_boundary
+        self.subdomain_boundaries = bnd
+        self.subdomain_boundaries_id_dict = id_dict
+
+    def _setup_boundaries_from_functions(self, boundary_dict):
+        bnd = fenics.MeshFunction("size_t", self._mesh, self.dim_geo - 1)
+        bnd.set_all(0)
+        ids = {}
+        for k, (name, sub) in enumerate(boundary_dict.items(), start=1):
+            self.logger.info("      - boundary '%s' with id=%d" % (name, k))
+            sub.mark(bnd, k)
+            ids[name] = k
+        self.named_boundaries_id_dict = ids
+        self.named_boundaries_function_dict = boundary_dict
+        self.named_boundaries = bnd
+
+    def add_named_boundaries(self, boundary_dict):
+        pass        # not implemented in the reference either (helper_classes.py:530-537)
+
+    def setup_measures(self):
+        self.dx = fenics.dx(subdomain_data=self.subdomains) if hasattr(self, "subdomains") else fenics.dx
+        self.ds = fenics.ds(subdomain_data=self.subdomain_boundaries) if hasattr(self, "subdomain_boundaries") else fenics.ds
+        self.dsn = fenics.ds(subdomain_data=self.named_boundaries) if hasattr(self, "named_boundaries") else fenics.ds
+
+    def create_discontinuous_scalar_from_parameter_map(self, param_dict, name, replace=False):
+        if not hasattr(self, "tissue_id_name_map"):
+            self.logger.warning("No subdomains have been defined, cannot assign parameter values")
+            return None
+        if not hasattr(self, "subdomains"):
+            self.logger.warning("No subdomains have been defined, cannot assign parameter values")
+            return None
+        if hasattr(self, name) and not replace:
+            self.logger.warning("Parameter '%s' already exists ... do nothing." % name)
+            return None
+        by_label = {lid: param_dict[lname] for lid, lname in self.tissue_id_name_map.items()}
+        ds = DiscontinuousScalar(self.subdomains, by_label, name=name)
+        setattr(self, name, ds)
+        return ds
+
+    def _create_tissue_name_id_map(self):
+        if hasattr(self, "tissue_id_name_map"):
+            self.tissue_name_id_map = {v: k for k, v in self.tissue_id_name_map.items()}
+
+    def get_subdomain_id(self, subdomain_name):
+        if not hasattr(self, "tissue_name_id_map"):
+            self._create_tissue_name_id_map()
+        if subdomain_name in getattr(self, "tissue_name_id_map", {}):
+            return self.tissue_name_id_map[subdomain_name]
+        self.logger.error("Subdomain '%s' does not exist" % subdomain_name)
+        return None
+
+
+# ==================================================================================================
+class BoundaryConditions:
+    """Dirichlet / von-Neumann dict specifications -> DirichletBC list and facet load terms
+    (helper_classes.py:618-908)."""
+
+    def __init__(self, functionspace, subdomains):
+        self.logger = logging.getLogger(__name__)
+        self._functionspace, self._subdomains = functionspace, subdomains
+
+    def setup_dirichlet_boundary_conditions(self, dirichlet_bcs=None):
+        dirichlet_bcs = dirichlet_bcs or {}
+        if len(dirichlet_bcs) > 0:
+            self.dirichlet_bcs_dict = dirichlet_bcs
+            self.dirichlet_bcs = []
+            for name, spec in dirichlet_bcs.items():
+                self.logger.info("     - Dirichlet BC '%s'" % name)
+                bc = self._construct_dirichlet_bc(spec)
+                if bc is not None:
+                    self.dirichlet_bcs.append(bc)
+
+    def _bc_space(self, spec):
+        if self._functionspace.has_subspaces:
+            if "subspace_id" not in spec:
+                self.logger.error("Dirichlet BC dictionary does not contain id of function sub space 'subspace_id'")
+                return None
+            return self._functionspace.get_functionspace_orig_subspace(subspace_id=spec["subspace_id"])
+        return self._functionspace.get_functionspace()
+
+    def _construct_dirichlet_bc(self, dirichlet_bc):
+        """Recognised boundary keys: 'boundary', 'subdomain_boundary', 'named_boundary'; anything else is
+        skipped with a warning (helper_classes.py:703-721, quirk Q1)."""
+        V = self._bc_space(dirichlet_bc)
+        value = dirichlet_bc["bc_value"]          # KeyError if absent, as in the reference (:697)
+        sd = self._subdomains
+        if "boundary" in dirichlet_bc:
+            return fenics.DirichletBC(V, value, dirichlet_bc["boundary"])
+        if "subdomain_boundary" in dirichlet_bc:
+            bid = sd.subdomain_boundaries_id_dict.get(dirichlet_bc["subdomain_boundary"])
+            return None if bid is None else fenics.DirichletBC(V, value, sd.subdomain_boundaries, bid)
+        if "named_boundary" in dirichlet_bc:
+            bid = sd.named_boundaries_id_dict.get(dirichlet_bc["named_boundary"])
+            return None if bid is None else fenics.DirichletBC(V, value, sd.named_boundaries, bid)
+        self.logger.warning("       - Dirichlet BC incomplete -- skipping")
+        return None
+
+    def setup_von_neumann_boundary_conditions(self, von_neumann_bcs=None):
+        von_neumann_bcs = von_neumann_bcs or {}
+        if len(von_neumann_bcs) > 0:
+            self.von_neumann_bcs_dict = von_neumann_bcs
+            out = {}
+            for name, spec in von_neumann_bcs.items():
+                s = self._construct_von_neumann_bc(spec)
+                if s is not None:
+                    out[name] = s
+            self.von_neumann_bcs = out
+
+    def _construct_von_neumann_bc(self, bc_dict):
+        value = bc_dict.get("bc_value")
+        if value is None:
+            self.logger.error("Von Neumann BC dictionary does not contain BC value, key 'bc_value'")
+        sid = bc_dict.get("subspace_id") if self._functionspace.has_subspaces else None
+        if self._functionspace.has_subspaces and sid is None:
+            self.logger.error("Von Neumann BC dictionary does not contain id of function subspace 'subspace_id'")
+        measure = None
+        sd = self._subdomains
+        if "boundary" in bc_dict:
+            self.logger.error("Function-based boundaries must be set up as 'named boundaries' upon initialisation.")
+        elif "subdomain_boundary" in bc_dict:
+            bid = sd.subdomain_boundaries_id_dict.get(bc_dict["subdomain_boundary"])
+            if bid is not None:
+                measure = sd.ds(bid)
+        elif "named_boundary" in bc_dict:
+            measure = sd.dsn(sd.named_boundaries_id_dict.get(bc_dict["named_boundary"]))
+        else:
+            self.logger.warning("       - Von Neumann BC incomplete -- skipping")
+        if value is not None and measure is not None and sid is not None:
+            return {"bc_value": value, "measure": measure, "subspace_id": sid}
+        return None
+
+    def time_update_bcs(self, time, kind="dirichlet"):
+        specs = getattr(self, "dirichlet_bcs_dict" if kind == "dirichlet" else "von_neumann_bcs_dict", {})
+        for name, bc in specs.items():
+            try:
+                bc["bc_value"].t = time
+            except Exception:
+                self.logger.debug("Updating %s BC '%s' at time %.2f raised exception" % (kind, name, time))
+
+    def neumann_terms(self, subspace_id):
+        """[(facet ids, subspace_id, value)] on *exterior* facets carrying the measure's id
+        (``ds`` integrates over exterior facets only, helper_classes.py:747-755)."""
+        out = []
+        for spec in getattr(self, "von_neumann_bcs", {}).values():
+            if spec["subspace_id"] != subspace_id:
+                continue
+            m = spec["measure"]
+            mesh = self._functionspace._mesh
+            ext = mesh.facets()[2][:, 1] < 0
+            fids = np.nonzero(ext & (np.asarray(m.subdomain_data.array()) == m.subdomain_id))[0]
+            out.append((fids, subspace_id, spec["bc_value"]))
+        return out
+
+    def implement_von_neumann_bc(self, product_component, subspace_id=None):
+        """Kept for API compatibility: returns the facet terms the backend integrates into the load vector."""
+        return self.neumann_terms(subspace_id)
+
+
+# ==================================================================================================
+class Parameters:
+    """Required/optional parameter plumbing, initial-value expressions, time update (helper_classes.py:910-1077)."""
+
+    def __init__(self, functionspace, subdomains, time_dependent=False):
+        self.logger = logging.getLogger(__name__)
+        self.time_dependent = time_dependent
+        self._functionspace, self._subdomains = functionspace, subdomains
+        self._iv_base_name = "iv"
+        if time_dependent:
+            self.sim_time = 1
+            self.sim_time_step = 1
+
+    def _get_iv_name(self, subspace_id=None):
+        if subspace_id is None:
+            return self._iv_base_name
+        return self._iv_base_name + "_" + self._functionspace.subspaces.names.get(subspace_id)
+
+    def get_iv(self, subspace_id):
+        name = self._get_iv_name(subspace_id)
+        if hasattr(self, name):
+            return getattr(self, name)
+        self.logger.warning("Initial value expression '%s' for subspace %s undefined" % (name, subspace_id))
+
+    def get_iv_map(self, return_name=True):
+        if self._functionspace.has_subspaces:
+            return {sid: (self._get_iv_name(sid) if return_name else self.get_iv(sid))
+                    for sid in self._functionspace.subspaces.get_subspace_ids()}
+        return self._get_iv_name() if return_name else self.get_iv(None)
+
+    def _set_iv(self, iv, subspace_id=None, replace=False):
+        name = self._get_iv_name(subspace_id)
+        if hasattr(self, name) and not replace:
+            self.logger.warning("Initial value expression '%s' already exists ... do nothing" % name)
+            return
+        setattr(self, name, iv)
+
+    def set_initial_value_expressions(self, ivs=None, replace=False):
+        for sid, iv in (ivs or {}).items():
+            self._set_iv(iv, sid, replace=replace)
+
+    def create_initial_value_function(self):
+        return self._functionspace.project_over_space(self.get_iv_map(return_name=False))
+
+    def define_required_params(self, params_name_list=None):
+        names = list(params_name_list or [])
+        if self.time_dependent:
+            names += ["sim_time", "sim_time_step"]
+        self.params_required = list(set(names))
+
+    def define_optional_params(self, params_name_list=None):
+        self.params_optional = list(set(params_name_list or []))
+
+    def _check_param_arguments(self, kw_args):
+        missing = set(self.params_required) - set(kw_args)
+        for p in set(kw_args) - set(self.params_required):
+            self.logger.info("    - parameter '%s' not needed" % p)
+        for p in missing:
+            self.logger.warning("    - parameter '%s' required but not available" % p)
+        return not missing
+
+    def set_parameter(self, param_name, param):
+        if isinstance(param, dict):
+            value = self._subdomains.create_discontinuous_scalar_from_parameter_map(param, param_name, replace=True)
+            setattr(self, param_name + "_dict", param)
+            setattr(self, param_name, value)
+        else:
+            setattr(self, param_name, param)
+
+    def get_parameter(self, param_name):
+        if hasattr(self, param_name):
+            return getattr(self, param_name)
+        self.logger.warning("Parameter '%s' has not been set." % param_name)
+        return None
+
+    def init_parameters(self, parameter_dict):
+        """Missing required parameters only log a warning and set nothing (helper_classes.py:1045-1053, quirk Q7)."""
+        if not self._check_param_arguments(parameter_dict):
+            self.logger.warning("Parameterset incomplete cannot initialize.")
+            return
+        for name, value in parameter_dict.items():
+            if name in self.params_required or name in self.params_optional:
+                self.set_parameter(name, value)
+            else:
+                self.logger.info("Parameter '%s' will be ignored." % name)
+
+    def time_update_parameters(self, time):
+        ivs = self.get_iv_map()
+        iv_names = ivs.values() if isinstance(ivs, dict) else [ivs]
+        for name in itertools.chain(self.params_required, self.params_optional, iv_names):
+            obj = getattr(self, name, None)
+            if obj is not None and not isinstance(obj, (int, float, dict, DiscontinuousScalar)):
+                try:
+                    obj.t = time
+                except Exception:
+                    pass
+
+
+# ==================================================================================================
+class TimeSeriesDataTimePoint:
+    def __init__(self, time, time_step, recording_step):
+        self.time, self.time_step, self.recording_step = time, time_step, recording_step
+
+    def set_field(self, field): self.field = field
+    def get_field(self): return getattr(self, "field", None)
+    def get_time(self): return self.time
+    def get_time_step(self): return self.time_step
+    def get_recording_step(self): return self.recording_step
+
+
+class TimeSeriesData:
+    """Deep copies of the solution per recording step (helper_classes.py:1110-1181)."""
+
+    def __init__(self, name, functionspace):
+        self.logger = logging.getLogger(__name__)
+        self._functionspace, self.name, self.data = functionspace, name, {}
+
+    def exists_recording_step(self, recording_step): return recording_step in self.data
+
+    def add_observation(self, field, time, time_step, recording_step, replace=False):
+        try:
+            copy = field.copy(deepcopy=True)
+        except Exception:
+            copy = self._functionspace.project_over_space(field)
+        obs = TimeSeriesDataTimePoint(time=time, time_step=time_step, recording_step=recording_step)
+        obs.set_field(copy)
+        if recording_step in self.data and not replace:
+            self.logger.warning("Recording step %i already exists" % recording_step)
+            return
+        self.data[recording_step] = obs
+
+    def get_observation(self, recording_step):
+        if recording_step in self.data:
+            return self.data[recording_step]
+        self.logger.warning("No solution available for recording step '%d'" % recording_step)
+
+    def get_all_recording_steps(self): return sorted(self.data)
+    def get_most_recent_observation(self): return self.get_observation(max(self.data))
+
+    def get_solution_function(self, subspace_name=None, subspace_id=None, recording_step=None):
+        obs = self.get_most_recent_observation() if recording_step is None else self.get_observation(recording_step)
+        if obs is None:
+            return None
+        sub = self._functionspace.split_function(obs.get_field(), subspace_id=subspace_id, subspace_name=subspace_name)
+        return self._functionspace.project_over_space(sub, subspace_name=subspace_name, subspace_id=subspace_id)
+
+
+class TimeSeriesMultiData:
+    """Named collection of time series + HDF5 round trip (helper_classes.py:1184-1308)."""
+
+    def __init__(self):
+        self.logger = logging.getLogger(__name__)
+        self.time_series_prefix = "tds_"
+        self._series = {}
+
+    def exists_time_series(self, name): return name in self._series
+    def get_all_time_series(self): return dict(self._series)
+
+    def exists_recording_step(self, name, recording_step):
+        return self.get_time_series(name).exists_recording_step(recording_step)
+
+    def register_time_series(self, name, functionspace, replace=False):
+        if name in self._series and not replace:
+            self.logger.warning("TimeSeries '%s' already exists" % name)
+            return
+        self._series[name] = TimeSeriesData(name=name, functionspace=functionspace)
+        setattr(self, self.time_series_prefix + name, self._series[name])
+
+    def get_time_series(self, name):
+        if name in self._series:
+            return self._series[name]
+        self.logger.warning("TimeSeries '%s' does not exist." % name)
+
+    def get_observation(self, name, recording_step):
+        ts = self.get_time_series(name)
+        return None if ts is None else ts.get_observation(recording_step)
+
+    def add_observation(self, name, field, time, time_step, recording_step, replace=False):
+        ts = self.get_time_series(name)
+        if ts is not None:
+            ts.add_observation(field, time, time_step, recording_step, replace=replace)
+
+    def get_solution_function(self, name, subspace_name=None, subspace_id=None, recording_step=None):
+        ts = self.get_time_series(name)
+        return None if ts is None else ts.get_solution_function(subspace_name, subspace_id, recording_step)
+
+    def get_all_recording_steps(self, name):
+        ts = self.get_time_series(name)
+        return None if ts is None else ts.get_all_recording_steps()
+
+    def _get_mpi_comm(self):
+        return None
+
+    def save_to_hdf5(self, path_to_file, replace=False):
+        """``/<name>/vector_<k>`` datasets with ``timestamp`` attributes and ``count`` on the group
+        (helper_classes.py:1256-1276; DOLFIN ``HDF5File.write(function, name, t)`` layout)."""
+        if os.path.exists(path_to_file) and not replace:
+            path_to_file = "test.h5"
+            self.logger.warning("Creating file with different name '%s'." % path_to_file)
+        hdf = fenics.HDF5File(self._get_mpi_comm(), path_to_file, "w")
+        for name in self._series:
+            for rs in self.get_all_recording_steps(name):
+                ts = self.get_observation(name, rs).get_time_step()
+                f = self.get_solution_function(name, subspace_name=None, recording_step=rs)
+                if f is not None:
+                    hdf.write(f, name, ts)
+        hdf.close()
+
+    def _create_empty_function(self, name, subspace_id=None, subspace_name=None):
+        ts = self.get_time_series(name)
+        if ts is not None:
+            return fenics.Function(ts._functionspace.get_functionspace(subspace_id=subspace_id, subspace_name=subspace_name))
+
+    def load_from_hdf5(self, path_to_file):
+        if not os.path.exists(path_to_file):
+            self.logger.warning("File '%s' does not exist" % path_to_file)
+            return
+        hdf = fenics.HDF5File(self._get_mpi_comm(), path_to_file, "r")
+        for name in self._series:
+            n_steps = hdf.attributes(name)["count"]
+            for step in range(n_steps):
+                dataset = name + "/vector_%d" % step
+                t = hdf.attributes(dataset)["timestamp"]
+                f = self._create_empty_function(name)
+                hdf.read(f, dataset)
+                self.add_observation(name, f, time=t, time_step=t, recording_step=step)
+        hdf.close()
+
+
+class Results:
+    """In-memory record of the run + writers (helper_classes.py:1312-1453)."""
+
+    def __init__(self, functionspace, subdomains=None, output_dir=config.output_dir_simulation_tmp):
+        self.logger = logging.getLogger(__name__)
+        self._functionspace = functionspace
+        self.current_time_step = 0
+        self.set_save_output_dir(output_dir)
+        self.ts_name = "solution"
+        self.data = TimeSeriesMultiData()
+        self.data.register_time_series(self.ts_name, functionspace=functionspace)
+        if subdomains is not None:
+            self._subdomains = subdomains
+
+    def set_save_output_dir(self, output_dir):
+        self.output_dir = output_dir
+        os.makedirs(output_dir, exist_ok=True)
+
+    def add_to_results(self, current_sim_time, current_time_step, recording_step, field, replace=False):
+        self.data.add_observation(name=self.ts_name, time=current_sim_time, time_step=current_time_step,
+                                  recording_step=recording_step, field=field, replace=replace)
+
+    def exists_recording_step(self, recording_step): return self.data.exists_recording_step(self.ts_name, recording_step)
+    def get_result(self, recording_step): return self.data.get_observation(self.ts_name, recording_step)
+    def get_recording_steps(self): return self.data.get_all_recording_steps(self.ts_name)
+
+    def get_solution_function(self, subspace_name=None, subspace_id=None, recording_step=None):
+        return self.data.get_solution_function(self.ts_name, subspace_name=subspace_name, subspace_id=subspace_id,
+                                               recording_step=recording_step)
+
+    def get_function_save_name(self, function_name, recording_step, method="vtk"):
+        return "solution_xdmf" if method == "xdmf" else "%s_%05d" % (function_name, recording_step)
+
+    def save_function(self, function, function_name, function_save_name, time, subspace_id=None, method="xdmf"):
+        if isinstance(function, fenics.MeshFunction):
+            local = function
+        elif isinstance(function, fenics.Function):
+            local = function.copy(deepcopy=True)
+        else:
+            local = self._functionspace.project_over_space(function, subspace_id=subspace_id)
+        local.rename(function_name, "label")
+        if method == "xdmf":
+            if not hasattr(self, "output_xdmf_file"):
+                path = os.path.join(self.output_dir, function_save_name + ".xdmf")
+                self.output_xdmf_file = fenics.XDMFFile(None, path)
+            self.output_xdmf_file.write_checkpoint(local, function_name, time)
+        elif method == "vtk":
+            path = os.path.join(self.output_dir, function_name, function_save_name + ".pvd")
+            _ensure_dir(path)
+            fenics.File(path) << (local, float(time))
+        else:
+            self.logger.warning("Save method '%s' is not defined" % method)
+
+    def save_solution(self, recording_step, time, function=None, method="xdmf"):
+        if method is None:
+            return
+        if function is None:
+            function = self.get_solution_function(recording_step=recording_step)
+        fs = self._functionspace
+        if fs.has_subspaces:
+            for sid in fs.subspaces.get_subspace_ids():
+                name = fs.subspaces.get_subspace_name(sid)
+                self.save_function(fs.split_function(function, subspace_id=sid), name,
+                                   self.get_function_save_name(name, recording_step, method), time, sid, method=method)
+        else:
+            self.save_function(function, fs.name, self.get_function_save_name(fs.name, recording_step, method), time,
+                               method=method)
+
+    def save_label_function(self, recording_step, time, method="xdmf"):
+        name = "label_map"
+        self.save_function(self._subdomains.subdomains, name, self.get_function_save_name(name, recording_step, method),
+                           time, method=method)
+
+    def save_solution_start(self, method="xdmf", clear_all=False):
+        if method is None:
+            return
+        if os.path.exists(self.output_dir) and clear_all:
+            shutil.rmtree(self.output_dir, ignore_errors=True)
+        os.makedirs(self.output_dir, exist_ok=True)
+        if method == "xdmf":
+            for ext in (".xdmf", ".h5"):
+                p = os.path.join(self.output_dir, "solution" + ext)
+                if os.path.isfile(p):
+                    os.remove(p)
+            self.output_xdmf_file = fenics.XDMFFile(None, os.path.join(self.output_dir, "solution.xdmf"))
+            self.output_xdmf_file.write(self._functionspace._mesh)
+        if hasattr(self, "_subdomains") and method == "vtk":
+            self.save_label_function(0, 0, method=method)
+
+    def save_solution_hdf5(self, save_path=None):
+        if save_path is None:
+            save_path = os.path.join(self.output_dir, "solution_timeseries.h5")
+        _ensure_dir(save_path)
+        self.data.save_to_hdf5(save_path, replace=True)
+
+    def save_solution_end(self, method="xdmf"):
+        if method == "xdmf" and hasattr(self, "output_xdmf_file"):
+            self.output_xdmf_file.close()
+
+
+class Plotting:
+    """Plotting is out of scope (matplotlib is not a dependency): ``plot=True`` is
+    tolerated -- one warning, then skipped (quirk Q9)."""
+
+    def __init__(self, results, output_dir=None):
+        self.logger = logging.getLogger(__name__)
+        self._warned = False
+
+    def plot_all(self, recording_step, **kw):
+        if not self._warned:
+            self.logger.warning("plotting is not part of the B200 hot path -- skipping plots")
+            self._warned = True
+
+
+class PostProcessTumorGrowth:
+    """Derived-field post-processing is a 'next' row; the handle exists so that
+    ``sim.init_postprocess`` does not fail, but it computes nothing yet."""
+
+    def __init__(self, results, params, output_dir=None, plot_params=None):
+        self.results, self.params, self.output_dir = results, params, output_dir
+
+    def __getattr__(self, name):
+        raise NotImplementedError("PostProcess.%s: derived fields are not implemented in the B200 backend yet" % name)
+
+
+PostProcessTumorGrowthBrain = PostProcessTumorGrowth
