@@ -205,5 +205,5 @@ class NonlinearVariationalSolver:
     def note_previous_assigned(self, u_previous, solution):
         """Called by the time loop after ``u_previous.assign(solution)``: the device already holds that copy,
         so the next solve need not upload it again."""
-        if getattr(self, "_device_prev_is", None) == solution.version and np.shares_memory(solution._x, solution._x):
+        if getattr(self, "_device_prev_is", None) == solution.version:
             self._pushed_version = (self._pushed_version[0], (id(u_previous), u_previous.version))

@@ -9,7 +9,7 @@ from glimslib_b200.backend.core import *            # noqa: F401,F403
 from glimslib_b200.backend.core import __version__  # noqa: F401
 from glimslib_b200.backend.io import HDF5File, XDMFFile, File  # noqa: F401
 from glimslib_b200.backend.problem import (NonlinearVariationalProblem, NonlinearVariationalSolver,  # noqa: F401
-                                            CoupledRDMechanicsForm)
+                                            CoupledRDMechanicsForm, SolverNotConverged)
 from glimslib_b200 import config
 
 if config.USE_ADJOINT:
