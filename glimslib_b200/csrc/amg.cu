@@ -1,6 +1,560 @@
-// Aggregation AMG for K_uu (placeholder until the real hierarchy lands: falls back to block-Jacobi).
+// Aggregation AMG preconditioner for the constant elasticity block K_uu (K5).
+//
+// Hierarchy: greedy vertex aggregation (host, on the vertex graph); tentative prolongator built from the
+// rigid-body modes of each aggregate about its centroid -- d translations + (1 | 3) rotations, so coarse
+// levels carry 3 (2D) or 6 (3D) unknowns per aggregate; Galerkin operators P^T A P accumulated on the
+// device into SELL-32 block matrices; Chebyshev(D^-1 A) smoothing with block-Jacobi D; dense inverse on the
+// coarsest level.  Everything in the V-cycle is a device kernel on the context stream: no host sync.
+// Fully constrained (Dirichlet) vertices and ghost vertices are left out of the coarse space, so on a
+// partitioned mesh the preconditioner is rank-local (block-Jacobi over sub-domains) with no communication.
 #include "common.h"
-struct Amg { int dummy; };
-void amg_setup(glims_ctx* c) { (void)c; }
-void amg_free(glims_ctx* c) { delete c->amg; c->amg = nullptr; }
-void amg_vcycle(glims_ctx* c, const double* r, double* z) { (void)c; (void)r; (void)z; }
+#include <thrust/device_ptr.h>
+#include <thrust/device_vector.h>
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblk(i64 n, int t = TPB) { return (int)((n + t - 1) / t); }
+
+struct Level {
+    int bs = 0;                 // unknowns per node on this level
+    int n = 0;                  // nodes (block rows)
+    i64 n_cols = 0;             // length of x in nodes (level 0: local vertices incl. ghosts)
+    SellPattern pat;
+    bool owns_pat = false;
+    double* A = nullptr;        // [n_slots][bs*bs] SELL value layout
+    bool owns_A = false;
+    double* dinv = nullptr;     // [n][bs*bs]
+    double lmax = 0;
+    // transfer to the next (coarser) level
+    int bsc = 0, nc = 0;
+    int* agg = nullptr;         // [n_cols] aggregate of node, -1 = not in the coarse space
+    double* rvec = nullptr;     // [n][dim] node position minus aggregate centroid
+    unsigned char* free_mask = nullptr;   // level 0: bit k set <=> dof k is free
+    int *mem_ptr = nullptr, *mem_idx = nullptr;   // members of each aggregate
+    double* X = nullptr;        // [n][dim] node positions
+    // work vectors
+    double *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
+};
+
+}  // namespace
+
+struct Amg {
+    int dim = 0;
+    std::vector<Level> L;
+    double* coarse_inv = nullptr;
+    int coarse_m = 0;
+    int cheb_degree = 2;
+    double cheb_ratio = 0.1;
+};
+
+namespace {
+
+// ---- small dense helpers on the device ------------------------------------------------------------
+// P_i (bs_f x bsc): level 0: diag(free) [I_d | R(r)] ; higher levels: [[I_d, R(r)], [0, I_rot]]
+template <int D>
+__device__ inline void build_P(bool level0, const double* r, unsigned mask, double (&P)[6][6], int& bsf, int& bsc) {
+    constexpr int NR = (D == 2) ? 1 : 3;
+    bsc = D + NR;
+    bsf = level0 ? D : bsc;
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) P[i][j] = 0.0;
+    for (int i = 0; i < D; ++i) P[i][i] = 1.0;
+    if (D == 2) { P[0][2] = -r[1]; P[1][2] = r[0]; }
+    else {
+        P[0][4] = r[2];  P[0][5] = -r[1];
+        P[1][3] = -r[2]; P[1][5] = r[0];
+        P[2][3] = r[1];  P[2][4] = -r[0];
+    }
+    if (level0) {
+        for (int i = 0; i < D; ++i)
+            if (!((mask >> i) & 1u)) for (int j = 0; j < 6; ++j) P[i][j] = 0.0;
+    } else {
+        for (int k = 0; k < NR; ++k) P[D + k][D + k] = 1.0;
+    }
+}
+
+// keys of the coarse pattern: one per fine slot
+__global__ void k_coarse_keys(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
+                              const int* __restrict__ col, int n_rows, const int* __restrict__ agg,
+                              unsigned long long* keys) {
+    const int S = blockIdx.x;
+    const i64 base = slice_off[S];
+    const int w = slice_w[S];
+    for (int t = threadIdx.x; t < w * 32; t += blockDim.x) {
+        const int r = S * 32 + (t & 31);
+        unsigned long long key = ~0ULL;
+        if (r < n_rows) {
+            int I = agg[r], J = agg[col[base + t]];
+            if (I >= 0 && J >= 0) key = ((unsigned long long)(unsigned)I << 32) | (unsigned)J;
+        }
+        keys[base + t] = key;
+    }
+}
+
+template <int D>
+__global__ void k_galerkin(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
+                           const int* __restrict__ col, int n_rows, bool level0, const double* __restrict__ A,
+                           const int* __restrict__ agg, const double* __restrict__ rvec,
+                           const unsigned char* __restrict__ free_mask, const unsigned long long* __restrict__ ukeys,
+                           const i64* __restrict__ c_rowptr, const i64* __restrict__ c_slice_off, double* Ac) {
+    const int S = blockIdx.x;
+    const i64 base = slice_off[S];
+    const int w = slice_w[S];
+    for (int t = threadIdx.x; t < w * 32; t += blockDim.x) {
+        const int r = S * 32 + (t & 31);
+        if (r >= n_rows) continue;
+        const i64 s = base + t;
+        const int cj = col[s];
+        const int I = agg[r], J = agg[cj];
+        if (I < 0 || J < 0) continue;
+        double Pi[6][6], Pj[6][6];
+        int bsf, bsc;
+        build_P<D>(level0, rvec + (i64)r * D, level0 ? free_mask[r] : 0xffu, Pi, bsf, bsc);
+        build_P<D>(level0, rvec + (i64)cj * D, level0 ? free_mask[cj] : 0xffu, Pj, bsf, bsc);
+        double a[6][6];
+        bool nz = false;
+        for (int i = 0; i < bsf; ++i)
+            for (int j = 0; j < bsf; ++j) { a[i][j] = A[vidx(s, i * bsf + j, bsf * bsf)]; nz |= (a[i][j] != 0.0); }
+        if (!nz) continue;
+        double B[6][6];   // A Pj
+        for (int i = 0; i < bsf; ++i)
+            for (int j = 0; j < bsc; ++j) {
+                double v = 0;
+                for (int k = 0; k < bsf; ++k) v += a[i][k] * Pj[k][j];
+                B[i][j] = v;
+            }
+        // coarse slot
+        unsigned long long key = ((unsigned long long)(unsigned)I << 32) | (unsigned)J;
+        i64 lo = c_rowptr[I], hi = c_rowptr[I + 1];
+        while (lo < hi) { i64 mid = (lo + hi) >> 1; if (ukeys[mid] < key) lo = mid + 1; else hi = mid; }
+        i64 cs = c_slice_off[I >> 5] + (lo - c_rowptr[I]) * 32 + (I & 31);
+        for (int i = 0; i < bsc; ++i)
+            for (int j = 0; j < bsc; ++j) {
+                double v = 0;
+                for (int k = 0; k < bsf; ++k) v += Pi[k][i] * B[k][j];
+                if (v != 0.0) atomicAdd(&Ac[vidx(cs, i * bsc + j, bsc * bsc)], v);
+            }
+    }
+}
+
+// r_c[I] = sum_{i in I} P_i^T r_f[i]   (one thread per aggregate, fixed order: deterministic)
+template <int D>
+__global__ void k_restrict(int nc, const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx, bool level0,
+                           const double* __restrict__ rvec, const unsigned char* __restrict__ free_mask,
+                           const double* __restrict__ rf, double* __restrict__ rc) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nc) return;
+    constexpr int NR = (D == 2) ? 1 : 3;
+    const int bsc = D + NR, bsf = level0 ? D : bsc;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int m = mem_ptr[I]; m < mem_ptr[I + 1]; ++m) {
+        const int i = mem_idx[m];
+        double P[6][6];
+        int a_, b_;
+        build_P<D>(level0, rvec + (i64)i * D, level0 ? free_mask[i] : 0xffu, P, a_, b_);
+        for (int k = 0; k < bsf; ++k) {
+            double v = rf[(i64)i * bsf + k];
+            for (int j = 0; j < bsc; ++j) acc[j] += P[k][j] * v;
+        }
+    }
+    for (int j = 0; j < bsc; ++j) rc[(i64)I * bsc + j] = acc[j];
+}
+
+// x_f[i] += P_i x_c[agg[i]]
+template <int D>
+__global__ void k_prolong_add(int n, const int* __restrict__ agg, bool level0, const double* __restrict__ rvec,
+                              const unsigned char* __restrict__ free_mask, const double* __restrict__ xc,
+                              double* __restrict__ xf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int I = agg[i];
+    if (I < 0) return;
+    constexpr int NR = (D == 2) ? 1 : 3;
+    const int bsc = D + NR, bsf = level0 ? D : bsc;
+    double P[6][6];
+    int a_, b_;
+    build_P<D>(level0, rvec + (i64)i * D, level0 ? free_mask[i] : 0xffu, P, a_, b_);
+    for (int k = 0; k < bsf; ++k) {
+        double v = 0;
+        for (int j = 0; j < bsc; ++j) v += P[k][j] * xc[(i64)I * bsc + j];
+        xf[(i64)i * bsf + k] += v;
+    }
+}
+
+// Chebyshev step: z = Dinv r ; d = c1 d + c2 z ; x += d      (first step: c1 = 0)
+template <int BS>
+__global__ void k_cheb_update(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ d,
+                              double* __restrict__ x, int n, double c1, double c2) {
+    for (i64 row = blockIdx.x * (i64)TPB + threadIdx.x; row < n; row += (i64)gridDim.x * TPB) {
+        double rv[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) rv[i] = r[row * BS + i];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            double z = 0;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) z += dinv[row * BS * BS + i * BS + j] * rv[j];
+            double dn = c2 * z + (c1 != 0.0 ? c1 * d[row * BS + i] : 0.0);
+            d[row * BS + i] = dn;
+            x[row * BS + i] += dn;
+        }
+    }
+}
+
+template <int BS>
+__global__ void k_block_diag_inverse(const int* __restrict__ diag, int n, const double* __restrict__ A, double* out,
+                                     double reg) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    i64 s = diag[r];
+    double a[BS][BS], inv[BS][BS];
+    double scale = 0;
+    for (int i = 0; i < BS; ++i)
+        for (int j = 0; j < BS; ++j) { a[i][j] = A[vidx(s, i * BS + j, BS * BS)]; inv[i][j] = i == j; }
+    for (int i = 0; i < BS; ++i) scale = fmax(scale, fabs(a[i][i]));
+    // rows with an empty diagonal (node outside the coarse space / fully constrained) -> identity
+    for (int i = 0; i < BS; ++i) if (a[i][i] == 0.0) a[i][i] = scale > 0 ? scale : 1.0;
+    // coarse blocks of tiny aggregates can be rank deficient (a rotation that moves no member): Tikhonov shift
+    for (int i = 0; i < BS; ++i) a[i][i] += reg * scale;
+    for (int p = 0; p < BS; ++p) {     // Gauss-Jordan with partial pivoting
+        int piv = p; double best = fabs(a[p][p]);
+        for (int i = p + 1; i < BS; ++i) if (fabs(a[i][p]) > best) { best = fabs(a[i][p]); piv = i; }
+        if (piv != p) for (int j = 0; j < BS; ++j) { double t = a[p][j]; a[p][j] = a[piv][j]; a[piv][j] = t; t = inv[p][j]; inv[p][j] = inv[piv][j]; inv[piv][j] = t; }
+        double ip = 1.0 / a[p][p];
+        for (int j = 0; j < BS; ++j) { a[p][j] *= ip; inv[p][j] *= ip; }
+        for (int i = 0; i < BS; ++i) {
+            if (i == p) continue;
+            double f = a[i][p];
+            for (int j = 0; j < BS; ++j) { a[i][j] -= f * a[p][j]; inv[i][j] -= f * inv[p][j]; }
+        }
+    }
+    for (int i = 0; i < BS; ++i) for (int j = 0; j < BS; ++j) out[(i64)r * BS * BS + i * BS + j] = inv[i][j];
+}
+
+__global__ void k_dense_matvec(const double* __restrict__ M, const double* __restrict__ x, double* __restrict__ y, int m) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= m) return;
+    double s = 0;
+    for (int j = lane; j < m; j += 32) s += M[(i64)row * m + j] * x[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+}
+
+__global__ void k_fill_pseudo_random(double* v, i64 n) {
+    i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long z = (unsigned long long)i * 0x9E3779B97F4A7C15ULL + 0x1234567ULL;
+    z ^= z >> 31; z *= 0xBF58476D1CE4E5B9ULL; z ^= z >> 29;
+    v[i] = (double)(z & 0xffffff) / (double)0xffffff - 0.5;
+}
+
+// ---- host helpers -----------------------------------------------------------------------------------
+struct HostGraph { std::vector<i64> rowptr; std::vector<int> col; };
+
+HostGraph download_graph(const SellPattern& p) {
+    HostGraph g;
+    g.rowptr.resize(p.n_rows + 1);
+    std::vector<i64> so(p.n_slices + 1);
+    std::vector<int> scol(p.n_slots);
+    GL_CUDA(cudaMemcpy(g.rowptr.data(), p.rowptr, sizeof(i64) * (p.n_rows + 1), cudaMemcpyDeviceToHost));
+    GL_CUDA(cudaMemcpy(so.data(), p.slice_off, sizeof(i64) * (p.n_slices + 1), cudaMemcpyDeviceToHost));
+    GL_CUDA(cudaMemcpy(scol.data(), p.col, sizeof(int) * p.n_slots, cudaMemcpyDeviceToHost));
+    g.col.resize(p.nnzb);
+    for (i64 r = 0; r < p.n_rows; ++r)
+        for (i64 t = g.rowptr[r]; t < g.rowptr[r + 1]; ++t)
+            g.col[t] = scol[so[r >> 5] + (t - g.rowptr[r]) * 32 + (r & 31)];
+    return g;
+}
+
+// Greedy (Vanek-style) aggregation; excluded[i] nodes stay out (-1). Returns number of aggregates.
+int aggregate(const HostGraph& g, int n, const std::vector<char>& excluded, std::vector<int>& agg) {
+    agg.assign(n, -1);
+    int na = 0;
+    auto nbr_ok = [&](int j) { return j < n && !excluded[j]; };
+    // pass 1: a node whose whole (eligible) neighbourhood is free becomes a root
+    for (int i = 0; i < n; ++i) {
+        if (excluded[i] || agg[i] >= 0) continue;
+        bool all_free = true;
+        int cnt = 0;
+        for (i64 t = g.rowptr[i]; t < g.rowptr[i + 1]; ++t) {
+            int j = g.col[t];
+            if (j == i || !nbr_ok(j)) continue;
+            ++cnt;
+            if (agg[j] >= 0) { all_free = false; break; }
+        }
+        if (!all_free || cnt == 0) continue;
+        agg[i] = na;
+        for (i64 t = g.rowptr[i]; t < g.rowptr[i + 1]; ++t) { int j = g.col[t]; if (j != i && nbr_ok(j)) agg[j] = na; }
+        ++na;
+    }
+    // pass 2: attach leftovers to a neighbouring aggregate (as decided after pass 1)
+    std::vector<int> agg1 = agg;
+    for (int i = 0; i < n; ++i) {
+        if (excluded[i] || agg1[i] >= 0) continue;
+        for (i64 t = g.rowptr[i]; t < g.rowptr[i + 1]; ++t) {
+            int j = g.col[t];
+            if (j != i && nbr_ok(j) && agg1[j] >= 0) { agg[i] = agg1[j]; break; }
+        }
+    }
+    // pass 3: remaining nodes form aggregates with their remaining neighbours
+    for (int i = 0; i < n; ++i) {
+        if (excluded[i] || agg[i] >= 0) continue;
+        agg[i] = na;
+        for (i64 t = g.rowptr[i]; t < g.rowptr[i + 1]; ++t) { int j = g.col[t]; if (j != i && nbr_ok(j) && agg[j] < 0) agg[j] = na; }
+        ++na;
+    }
+    return na;
+}
+
+void alloc_work(Level& l) {
+    i64 n = std::max<i64>(l.n_cols, l.n) * l.bs;
+    for (double** v : {&l.x, &l.b, &l.r, &l.d}) {
+        GL_CUDA(cudaMalloc(v, sizeof(double) * (n > 0 ? n : 1)));
+        GL_CUDA(cudaMemset(*v, 0, sizeof(double) * (n > 0 ? n : 1)));
+    }
+}
+
+void diag_inverse(glims_ctx* c, Level& l, double reg) {
+    GL_CUDA(cudaMalloc(&l.dinv, sizeof(double) * (i64)l.n * l.bs * l.bs));
+    int g = nblk(l.n);
+    if (l.bs == 2) k_block_diag_inverse<2><<<g, TPB, 0, c->stream>>>(l.pat.diag, l.n, l.A, l.dinv, reg);
+    else if (l.bs == 3) k_block_diag_inverse<3><<<g, TPB, 0, c->stream>>>(l.pat.diag, l.n, l.A, l.dinv, reg);
+    else k_block_diag_inverse<6><<<g, TPB, 0, c->stream>>>(l.pat.diag, l.n, l.A, l.dinv, reg);
+}
+
+void estimate_lmax(glims_ctx* c, Level& l) {
+    i64 n = (i64)l.n * l.bs;
+    k_fill_pseudo_random<<<nblk(n), TPB, 0, c->stream>>>(l.x, n);
+    double lam = 1.0;
+    for (int it = 0; it < 15; ++it) {
+        launch_spmv_generic(c, l.pat, l.A, l.bs, l.x, l.r);
+        launch_block_jacobi(c, l.dinv, l.bs, l.r, l.d, l.n, -1);
+        launch_dot(c, l.d, l.d, n, S_TMP0);
+        launch_dot(c, l.x, l.x, n, S_TMP1);
+        double v[2];
+        read_scalars(c, S_TMP0, 2, v);
+        lam = std::sqrt(v[0] / (v[1] > 0 ? v[1] : 1.0));
+        launch_copy(c, l.d, l.x, n);
+        launch_scale(c, 1.0 / std::sqrt(v[0] > 0 ? v[0] : 1.0), l.x, n);
+    }
+    l.lmax = 1.1 * lam;
+    launch_zero(c, l.x, std::max<i64>(l.n_cols, l.n) * l.bs);
+    launch_zero(c, l.d, std::max<i64>(l.n_cols, l.n) * l.bs);
+    launch_zero(c, l.r, std::max<i64>(l.n_cols, l.n) * l.bs);
+}
+
+template <int BS>
+void cheb_update(glims_ctx* c, Level& l, double* x, double c1, double c2) {
+    int g = (int)std::min<i64>((l.n + TPB - 1) / TPB, 148 * 8);
+    k_cheb_update<BS><<<g > 0 ? g : 1, TPB, 0, c->stream>>>(l.dinv, l.r, l.d, x, l.n, c1, c2);
+    c->launches++;
+}
+
+// x <- x + p(D^-1 A) D^-1 (b - A x), Chebyshev polynomial of the given degree on [ratio*lmax, lmax]
+void smooth(glims_ctx* c, Amg* amg, Level& l, const double* b, double* x, bool zero_guess) {
+    const double lmax = l.lmax, lmin = amg->cheb_ratio * lmax;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    for (int k = 0; k < amg->cheb_degree; ++k) {
+        if (k == 0 && zero_guess) {
+            GL_CUDA(cudaMemcpyAsync(l.r, b, sizeof(double) * (i64)l.n * l.bs, cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            launch_spmv_generic(c, l.pat, l.A, l.bs, x, l.r, b);
+        }
+        double c1, c2;
+        if (k == 0) { c1 = 0.0; c2 = 1.0 / theta; }
+        else {
+            double rho_new = 1.0 / (2.0 * sigma - rho);
+            c1 = rho_new * rho;
+            c2 = 2.0 * rho_new / delta;
+            rho = rho_new;
+        }
+        if (l.bs == 2) cheb_update<2>(c, l, x, c1, c2);
+        else if (l.bs == 3) cheb_update<3>(c, l, x, c1, c2);
+        else cheb_update<6>(c, l, x, c1, c2);
+    }
+}
+
+void vcycle(glims_ctx* c, Amg* amg, int li, const double* b, double* x) {
+    Level& l = amg->L[li];
+    const int D = amg->dim;
+    if (li == (int)amg->L.size() - 1) {
+        int m = amg->coarse_m;
+        k_dense_matvec<<<(m + 7) / 8, 256, 0, c->stream>>>(amg->coarse_inv, b, x, m);
+        c->launches++;
+        return;
+    }
+    Level& lc = amg->L[li + 1];
+    launch_zero(c, x, (i64)l.n * l.bs);
+    smooth(c, amg, l, b, x, true);
+    launch_spmv_generic(c, l.pat, l.A, l.bs, x, l.r, b);
+    const bool l0 = (li == 0);
+    if (D == 2) k_restrict<2><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r, lc.b);
+    else k_restrict<3><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r, lc.b);
+    c->launches++;
+    vcycle(c, amg, li + 1, lc.b, lc.x);
+    if (D == 2) k_prolong_add<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x, x);
+    else k_prolong_add<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x, x);
+    c->launches++;
+    smooth(c, amg, l, b, x, false);
+}
+
+void free_level(Level& l) {
+    if (l.owns_pat) free_pattern(l.pat);
+    if (l.owns_A && l.A) cudaFree(l.A);
+    for (void* q : {(void*)l.dinv, (void*)l.agg, (void*)l.rvec, (void*)l.free_mask, (void*)l.mem_ptr, (void*)l.mem_idx,
+                    (void*)l.X, (void*)l.x, (void*)l.b, (void*)l.r, (void*)l.d})
+        if (q) cudaFree(q);
+}
+
+}  // namespace
+
+void amg_free(glims_ctx* c) {
+    if (!c->amg) return;
+    for (auto& l : c->amg->L) free_level(l);
+    if (c->amg->coarse_inv) cudaFree(c->amg->coarse_inv);
+    delete c->amg;
+    c->amg = nullptr;
+}
+
+void amg_setup(glims_ctx* c) {
+    amg_free(c);
+    Amg* amg = new Amg();
+    c->amg = amg;
+    const int D = c->dim;
+    amg->dim = D;
+    const int bsc = (D == 2) ? 3 : 6;
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+
+    // ---- level 0 wraps K_uu ---------------------------------------------------------------------
+    Level l0;
+    l0.bs = D; l0.n = c->pat.n_rows; l0.n_cols = c->n_v; l0.pat = c->pat; l0.A = c->Kuu;
+    std::vector<double> X(c->n_v * D);
+    GL_CUDA(cudaMemcpy(X.data(), c->coords, sizeof(double) * c->n_v * D, cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> bcm(c->n_v);
+    GL_CUDA(cudaMemcpy(bcm.data(), c->bcmask, c->n_v, cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> freem(c->n_v);
+    const unsigned umask = (1u << D) - 1u;
+    for (i64 i = 0; i < c->n_v; ++i) freem[i] = (unsigned char)(~bcm[i] & umask);
+    GL_CUDA(cudaMalloc(&l0.free_mask, c->n_v));
+    GL_CUDA(cudaMemcpy(l0.free_mask, freem.data(), c->n_v, cudaMemcpyHostToDevice));
+    amg->L.push_back(l0);
+
+    std::vector<double> Xl = X;              // positions of the current level's nodes
+    int level = 0;
+    while (true) {
+        Level& l = amg->L[level];
+        alloc_work(l);
+        diag_inverse(c, l, level == 0 ? 0.0 : 1e-8);
+        const int n = l.n;
+        const bool last = (n * l.bs <= 600) || level >= 12;
+        if (last) break;
+        // ---- aggregation on the host ---------------------------------------------------------------
+        HostGraph g = download_graph(l.pat);
+        std::vector<char> excl(n, 0);
+        if (level == 0) for (int i = 0; i < n; ++i) excl[i] = (freem[i] == 0);
+        std::vector<int> agg;
+        int na = aggregate(g, n, excl, agg);
+        if (na == 0 || na >= n) break;
+        // centroids, offsets, member lists
+        std::vector<double> Xc((i64)na * D, 0.0);
+        std::vector<int> cnt(na, 0);
+        for (int i = 0; i < n; ++i) if (agg[i] >= 0) { cnt[agg[i]]++; for (int k = 0; k < D; ++k) Xc[(i64)agg[i] * D + k] += Xl[(i64)i * D + k]; }
+        for (int I = 0; I < na; ++I) for (int k = 0; k < D; ++k) Xc[(i64)I * D + k] /= cnt[I];
+        std::vector<double> rv((i64)std::max<i64>(l.n_cols, n) * D, 0.0);
+        for (int i = 0; i < n; ++i) if (agg[i] >= 0) for (int k = 0; k < D; ++k) rv[(i64)i * D + k] = Xl[(i64)i * D + k] - Xc[(i64)agg[i] * D + k];
+        std::vector<int> mptr(na + 1, 0), midx;
+        for (int I = 0; I < na; ++I) mptr[I + 1] = mptr[I] + cnt[I];
+        midx.resize(mptr[na]);
+        { std::vector<int> pos(mptr.begin(), mptr.end() - 1); for (int i = 0; i < n; ++i) if (agg[i] >= 0) midx[pos[agg[i]]++] = i; }
+        std::vector<int> aggfull(std::max<i64>(l.n_cols, n), -1);
+        std::copy(agg.begin(), agg.end(), aggfull.begin());
+        l.bsc = bsc; l.nc = na;
+        GL_CUDA(cudaMalloc(&l.agg, sizeof(int) * aggfull.size()));
+        GL_CUDA(cudaMemcpy(l.agg, aggfull.data(), sizeof(int) * aggfull.size(), cudaMemcpyHostToDevice));
+        GL_CUDA(cudaMalloc(&l.rvec, sizeof(double) * rv.size()));
+        GL_CUDA(cudaMemcpy(l.rvec, rv.data(), sizeof(double) * rv.size(), cudaMemcpyHostToDevice));
+        GL_CUDA(cudaMalloc(&l.mem_ptr, sizeof(int) * (na + 1)));
+        GL_CUDA(cudaMemcpy(l.mem_ptr, mptr.data(), sizeof(int) * (na + 1), cudaMemcpyHostToDevice));
+        GL_CUDA(cudaMalloc(&l.mem_idx, sizeof(int) * std::max<size_t>(midx.size(), 1)));
+        GL_CUDA(cudaMemcpy(l.mem_idx, midx.data(), sizeof(int) * midx.size(), cudaMemcpyHostToDevice));
+        // ---- Galerkin operator on the device -------------------------------------------------------
+        Level lc;
+        lc.bs = bsc; lc.n = na; lc.n_cols = na; lc.owns_pat = true; lc.owns_A = true;
+        unsigned long long *keys = nullptr, *ukeys = nullptr;
+        GL_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * std::max<i64>(l.pat.n_slots, 1)));
+        k_coarse_keys<<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, l.agg, keys);
+        build_pattern_from_keys(c->stream, keys, l.pat.n_slots, na, lc.pat, &ukeys);
+        cudaFree(keys);
+        GL_CUDA(cudaMalloc(&lc.A, sizeof(double) * lc.pat.n_slots * bsc * bsc));
+        GL_CUDA(cudaMemsetAsync(lc.A, 0, sizeof(double) * lc.pat.n_slots * bsc * bsc, c->stream));
+        if (D == 2) k_galerkin<2><<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, level == 0, l.A, l.agg, l.rvec, l.free_mask, ukeys, lc.pat.rowptr, lc.pat.slice_off, lc.A);
+        else k_galerkin<3><<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, level == 0, l.A, l.agg, l.rvec, l.free_mask, ukeys, lc.pat.rowptr, lc.pat.slice_off, lc.A);
+        GL_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(ukeys);
+        amg->L.push_back(lc);
+        Xl.swap(Xc);
+        ++level;
+    }
+    // ---- coarsest level: dense (regularised) inverse on the host --------------------------------------
+    {
+        Level& l = amg->L.back();
+        const int bs = l.bs, n = l.n, m = n * bs;
+        amg->coarse_m = m;
+        HostGraph g = download_graph(l.pat);
+        std::vector<double> Av((i64)l.pat.n_slots * bs * bs);
+        std::vector<i64> so(l.pat.n_slices + 1);
+        GL_CUDA(cudaMemcpy(Av.data(), l.A, sizeof(double) * Av.size(), cudaMemcpyDeviceToHost));
+        GL_CUDA(cudaMemcpy(so.data(), l.pat.slice_off, sizeof(i64) * so.size(), cudaMemcpyDeviceToHost));
+        std::vector<double> M((i64)m * m, 0.0), Inv((i64)m * m, 0.0);
+        for (int r = 0; r < n; ++r)
+            for (i64 t = g.rowptr[r]; t < g.rowptr[r + 1]; ++t) {
+                i64 s = so[r >> 5] + (t - g.rowptr[r]) * 32 + (r & 31);
+                int cj = g.col[t];
+                if (cj >= n) continue;
+                for (int i = 0; i < bs; ++i) for (int j = 0; j < bs; ++j)
+                    M[(i64)(r * bs + i) * m + cj * bs + j] = Av[vidx(s, i * bs + j, bs * bs)];
+            }
+        double dmax = 0;
+        for (int i = 0; i < m; ++i) dmax = std::max(dmax, std::fabs(M[(i64)i * m + i]));
+        if (dmax == 0) dmax = 1.0;
+        for (int i = 0; i < m; ++i) {
+            if (M[(i64)i * m + i] == 0.0) M[(i64)i * m + i] = dmax;     // empty rows (constrained nodes on a one-level hierarchy)
+            M[(i64)i * m + i] += 1e-10 * dmax;                          // floating sub-domains: regularise the rigid modes
+            Inv[(i64)i * m + i] = 1.0;
+        }
+        for (int p = 0; p < m; ++p) {
+            int piv = p; double best = std::fabs(M[(i64)p * m + p]);
+            for (int i = p + 1; i < m; ++i) if (std::fabs(M[(i64)i * m + p]) > best) { best = std::fabs(M[(i64)i * m + p]); piv = i; }
+            if (piv != p) for (int j = 0; j < m; ++j) { std::swap(M[(i64)p * m + j], M[(i64)piv * m + j]); std::swap(Inv[(i64)p * m + j], Inv[(i64)piv * m + j]); }
+            double ip = 1.0 / M[(i64)p * m + p];
+            for (int j = 0; j < m; ++j) { M[(i64)p * m + j] *= ip; Inv[(i64)p * m + j] *= ip; }
+            for (int i = 0; i < m; ++i) {
+                if (i == p) continue;
+                double f = M[(i64)i * m + p];
+                if (f == 0.0) continue;
+                for (int j = 0; j < m; ++j) { M[(i64)i * m + j] -= f * M[(i64)p * m + j]; Inv[(i64)i * m + j] -= f * Inv[(i64)p * m + j]; }
+            }
+        }
+        GL_CUDA(cudaMalloc(&amg->coarse_inv, sizeof(double) * std::max<i64>((i64)m * m, 1)));
+        GL_CUDA(cudaMemcpy(amg->coarse_inv, Inv.data(), sizeof(double) * (i64)m * m, cudaMemcpyHostToDevice));
+    }
+    // ---- smoother spectra ----------------------------------------------------------------------------
+    for (size_t li = 0; li + 1 < amg->L.size(); ++li) estimate_lmax(c, amg->L[li]);
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void amg_vcycle(glims_ctx* c, const double* r, double* z) {
+    Amg* amg = c->amg;
+    if (amg->L.size() == 1) {     // tiny problem: the dense inverse is the whole hierarchy
+        k_dense_matvec<<<(amg->coarse_m + 7) / 8, 256, 0, c->stream>>>(amg->coarse_inv, r, z, amg->coarse_m);
+        c->launches++;
+        return;
+    }
+    vcycle(c, amg, 0, r, z);
+}

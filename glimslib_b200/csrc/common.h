@@ -124,6 +124,11 @@ struct glims_ctx {
 // ---------------- pattern.cu
 void build_pattern(glims_ctx* c);
 void build_gather_map(glims_ctx* c);
+// SELL pattern from unsorted 64-bit (row<<32|col) keys on the device; ~0 keys are dropped. keys is consumed.
+// ukeys_out (optional) receives the sorted unique keys (device, caller frees), in CSR order.
+void build_pattern_from_keys(cudaStream_t st, unsigned long long* keys, i64 n_keys, i64 n_rows, SellPattern& P,
+                             unsigned long long** ukeys_out);
+void free_pattern(SellPattern& P);
 
 // ---------------- kernels.cu (launch wrappers; all on c->stream)
 void launch_assemble(glims_ctx* c, int what, int variant);
@@ -143,7 +148,8 @@ void launch_spmv(glims_ctx* c, int which, const double* x, double* y, SpmvDot do
 void launch_spmv_uc(glims_ctx* c, const double* xc, double* yu);
 
 // generic SELL block SpMV used by AMG levels: y = A x, A blocks BRxBC stored [slot][BR*BC]
-void launch_spmv_generic(glims_ctx* c, const SellPattern& p, const double* A, int bs, const double* x, double* y);
+void launch_spmv_generic(glims_ctx* c, const SellPattern& p, const double* A, int bs, const double* x, double* y,
+                         const double* rhs = nullptr);   // rhs: y = rhs - A x
 
 // vector kernels with device-resident scalars; scal indices refer to c->scal
 enum { S_RZ = 0, S_PAP, S_RR, S_RZNEW, S_BN, S_TMP0, S_TMP1, S_TMP2, S_TMP3, S_GM0 /* 64 slots from here */, S_COUNT = 128 };

@@ -352,11 +352,12 @@ __global__ void k_bc_diag(const i64* __restrict__ dofs, i64 n, i64 n_own, const 
 // ------------------------------------------------------------------------------------------------
 // K4 SpMV, SELL-32: one thread per block row, slice width uniform per warp, value loads coalesced
 // (component-major inside each 32-slot group), x gathered through L1/L2.
-template <int BR, int BC, bool DOT>
+template <int BR, int BC, bool DOT, bool RESID = false>
 __global__ void __launch_bounds__(TPB)
 k_spmv_block(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
              const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, int n_rows,
              const double* __restrict__ wdot, double* partials, unsigned* tickets, double* scal, int slot) {
+    // RESID: y = wdot - A x  (wdot doubles as the right-hand side; no dot product in that mode)
     double local[1] = {0.0};
     const int n_tiles = (n_rows + TPB - 1) / TPB;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -382,8 +383,13 @@ k_spmv_block(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
             }
         }
         if (r < n_rows) {
+            if (RESID) {
 #pragma unroll
-            for (int i = 0; i < BR; ++i) y[(i64)r * BR + i] = acc[i];
+                for (int i = 0; i < BR; ++i) y[(i64)r * BR + i] = wdot[(i64)r * BR + i] - acc[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < BR; ++i) y[(i64)r * BR + i] = acc[i];
+            }
             if (DOT) {
 #pragma unroll
                 for (int i = 0; i < BR; ++i) local[0] += acc[i] * wdot[(i64)r * BR + i];
@@ -798,9 +804,12 @@ void launch_spmv_uc(glims_ctx* c, const double* xc, double* yu) {
     else k_spmv_uc<3><<<nblk(p.n_slices * 32), TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuc, xc, yu, p.n_rows);
     LAUNCHED(c);
 }
-void launch_spmv_generic(glims_ctx* c, const SellPattern& p, const double* A, int bs, const double* x, double* y) {
+void launch_spmv_generic(glims_ctx* c, const SellPattern& p, const double* A, int bs, const double* x, double* y,
+                         const double* rhs) {
+    // rhs == nullptr: y = A x ; else y = rhs - A x
     int g = red_grid(c, p.n_rows);
-#define GEN(B) k_spmv_block<B, B, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, nullptr, c->partials, c->tickets, c->scal, 0)
+#define GEN(B) do { if (rhs) k_spmv_block<B, B, false, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, rhs, c->partials, c->tickets, c->scal, 0); \
+                    else k_spmv_block<B, B, false, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, nullptr, c->partials, c->tickets, c->scal, 0); } while (0)
     if (bs == 1) GEN(1); else if (bs == 2) GEN(2); else if (bs == 3) GEN(3); else if (bs == 6) GEN(6);
     else throw GlError(GLIMS_ERR_ARG, "spmv_generic: unsupported block size");
 #undef GEN

@@ -119,17 +119,14 @@ inline int nblk(i64 n, int t = 256) { return (int)((n + t - 1) / t); }
 
 }  // namespace
 
-void build_pattern_generic(cudaStream_t st, const int* cells, i64 n_c, int nb, i64 n_own, SellPattern& P, int** eslot_out) {
+void build_pattern_from_keys(cudaStream_t st, unsigned long long* kp, i64 np, i64 n_own, SellPattern& P,
+                             unsigned long long** ukeys_out) {
     auto pol = thrust::cuda::par.on(st);
-    i64 np = n_c * nb * nb;
-    thrust::device_vector<unsigned long long> keys(np);
-    unsigned long long* kp = thrust::raw_pointer_cast(keys.data());
-    k_gen_keys<<<nblk(np), 256, 0, st>>>(cells, n_c, nb, n_own, kp);
-    thrust::sort(pol, keys.begin(), keys.end());
-    auto uend = thrust::unique(pol, keys.begin(), keys.end());
-    i64 nu = uend - keys.begin();
-    // drop the sentinel if present
-    if (nu > 0) {
+    thrust::device_ptr<unsigned long long> keys(kp);
+    thrust::sort(pol, keys, keys + np);
+    auto uend = thrust::unique(pol, keys, keys + np);
+    i64 nu = uend - keys;
+    if (nu > 0) {   // drop the sentinel if present
         unsigned long long last;
         GL_CUDA(cudaMemcpyAsync(&last, kp + nu - 1, 8, cudaMemcpyDeviceToHost, st));
         GL_CUDA(cudaStreamSynchronize(st));
@@ -140,7 +137,7 @@ void build_pattern_generic(cudaStream_t st, const int* cells, i64 n_c, int nb, i
     P.n_slices = (int)((n_own + SLICE - 1) / SLICE);
     GL_CUDA(cudaMalloc(&P.rowptr, sizeof(i64) * (n_own + 1)));
     thrust::device_ptr<i64> rp(P.rowptr);
-    thrust::lower_bound(pol, keys.begin(), keys.begin() + nu,
+    thrust::lower_bound(pol, keys, keys + nu,
                         thrust::make_transform_iterator(thrust::counting_iterator<i64>(0), RowStart()),
                         thrust::make_transform_iterator(thrust::counting_iterator<i64>(n_own + 1), RowStart()), rp);
     GL_CUDA(cudaMalloc(&P.slice_w, sizeof(int) * P.n_slices));
@@ -158,9 +155,28 @@ void build_pattern_generic(cudaStream_t st, const int* cells, i64 n_c, int nb, i
     GL_CUDA(cudaMalloc(&P.diag, sizeof(int) * n_own));
     k_init_col<<<P.n_slices, 128, 0, st>>>(P.slice_off, P.slice_w, P.n_rows, P.n_slices, P.col);
     k_fill_col<<<nblk(nu), 256, 0, st>>>(kp, nu, P.rowptr, P.slice_off, P.col, P.diag);
+    if (ukeys_out) {
+        GL_CUDA(cudaMalloc(ukeys_out, sizeof(unsigned long long) * (nu > 0 ? nu : 1)));
+        GL_CUDA(cudaMemcpyAsync(*ukeys_out, kp, sizeof(unsigned long long) * nu, cudaMemcpyDeviceToDevice, st));
+    }
+    GL_CUDA(cudaStreamSynchronize(st));
+}
+
+void free_pattern(SellPattern& P) {
+    for (void* q : {(void*)P.slice_off, (void*)P.slice_w, (void*)P.col, (void*)P.rowptr, (void*)P.diag})
+        if (q) cudaFree(q);
+    P = SellPattern();
+}
+
+void build_pattern_generic(cudaStream_t st, const int* cells, i64 n_c, int nb, i64 n_own, SellPattern& P, int** eslot_out) {
+    i64 np = n_c * nb * nb;
+    thrust::device_vector<unsigned long long> keys(np);
+    unsigned long long* kp = thrust::raw_pointer_cast(keys.data());
+    k_gen_keys<<<nblk(np), 256, 0, st>>>(cells, n_c, nb, n_own, kp);
+    build_pattern_from_keys(st, kp, np, n_own, P, nullptr);
     if (eslot_out) {
         GL_CUDA(cudaMalloc(eslot_out, sizeof(int) * np));
-        k_eslot<<<nblk(np), 256, 0, st>>>(cells, n_c, nb, n_own, kp, nu, P.rowptr, P.slice_off, *eslot_out);
+        k_eslot<<<nblk(np), 256, 0, st>>>(cells, n_c, nb, n_own, kp, P.nnzb, P.rowptr, P.slice_off, *eslot_out);
     }
     GL_CUDA(cudaStreamSynchronize(st));
 }
