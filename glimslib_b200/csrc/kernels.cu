@@ -399,6 +399,46 @@ k_spmv_block(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
     if (DOT) grid_reduce<1>(local, partials, tickets, scal, slot);
 }
 
+// Coarse AMG levels: few rows, fat blocks. One CTA per slice, warp i computes block-row component i of the
+// slice's 32 rows, so a 6x6 level exposes 6x the parallelism of the thread-per-row kernel while every value
+// load stays a coalesced 256-byte warp access.  RESID: y = rhs - A x.
+template <int BS, bool RESID>
+__global__ void __launch_bounds__(32 * BS)
+k_spmv_split(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+             const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, int n_rows,
+             int n_slices, const double* __restrict__ rhs) {
+    const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
+    for (int S = blockIdx.x; S < n_slices; S += gridDim.x) {
+        const int r = S * 32 + lane;
+        const i64 base = slice_off[S];
+        const int w = slice_w[S];
+        double acc0 = 0.0, acc1 = 0.0;
+        int j = 0;
+        for (; j + 1 < w; j += 2) {      // two blocks in flight per thread
+            const i64 g0 = base + (i64)j * 32, g1 = g0 + 32;
+            const int c0 = __ldg(&col[g0 + lane]), c1 = __ldg(&col[g1 + lane]);
+            const double* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+            const double* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < BS; ++b) {
+                acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+                acc1 += __ldcs(&A1[b * 32]) * __ldg(&x[(i64)c1 * BS + b]);
+            }
+        }
+        if (j < w) {
+            const i64 g0 = base + (i64)j * 32;
+            const int c0 = __ldg(&col[g0 + lane]);
+            const double* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+        }
+        if (r < n_rows) {
+            const double v = acc0 + acc1;
+            y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - v : v;
+        }
+    }
+}
+
 // monolithic Jacobian J = [[K_uu, K_uc], [0, K_cc]] on vertex-blocked vectors [n_v][D+1]
 template <int D, bool DOT>
 __global__ void __launch_bounds__(TPB)
@@ -807,10 +847,18 @@ void launch_spmv_uc(glims_ctx* c, const double* xc, double* yu) {
 void launch_spmv_generic(glims_ctx* c, const SellPattern& p, const double* A, int bs, const double* x, double* y,
                          const double* rhs) {
     // rhs == nullptr: y = A x ; else y = rhs - A x
+    if (bs == 6) {     // coarse AMG levels: warp-per-component kernel
+        int g = p.n_slices < 148 * 16 ? p.n_slices : 148 * 16;
+        if (g < 1) g = 1;
+        if (rhs) k_spmv_split<6, true><<<g, 192, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, p.n_slices, rhs);
+        else k_spmv_split<6, false><<<g, 192, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, p.n_slices, nullptr);
+        LAUNCHED(c);
+        return;
+    }
     int g = red_grid(c, p.n_rows);
 #define GEN(B) do { if (rhs) k_spmv_block<B, B, false, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, rhs, c->partials, c->tickets, c->scal, 0); \
                     else k_spmv_block<B, B, false, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, nullptr, c->partials, c->tickets, c->scal, 0); } while (0)
-    if (bs == 1) GEN(1); else if (bs == 2) GEN(2); else if (bs == 3) GEN(3); else if (bs == 6) GEN(6);
+    if (bs == 1) GEN(1); else if (bs == 2) GEN(2); else if (bs == 3) GEN(3);
     else throw GlError(GLIMS_ERR_ARG, "spmv_generic: unsupported block size");
 #undef GEN
     LAUNCHED(c);

@@ -480,7 +480,9 @@ int glims_step(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, glims_
     if (!o) { glims_default_opts(&od); o = &od; }
     for (int s = 0; s < n_steps; ++s) {
         newton_step(c, o, stats ? &stats[s] : nullptr);
-        // u_previous.assign(solution)  (simulation_base.py:312)
+        // u_previous.assign(solution)  (simulation_base.py:312); ghosts refreshed first so that the next
+        // step's residual sees the converged c_prev on the overlap cells
+        halo_exchange(c, c->x, c->nb);
         launch_copy(c, c->x, c->xprev, c->ndof);
     }
     GL_CUDA(cudaStreamSynchronize(c->stream));
