@@ -21,6 +21,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line (NCCL prints its version otherwise)
 
 METRIC = "timesteps/sec, 3D 10M-tet coupled RD-mechanics (config C4)"
 UNIT = "timesteps/s"

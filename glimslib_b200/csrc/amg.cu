@@ -356,7 +356,7 @@ void cheb_update(glims_ctx* c, Level& l, double* x, double c1, double c2) {
 }
 
 // x <- x + p(D^-1 A) D^-1 (b - A x), Chebyshev polynomial of the given degree on [ratio*lmax, lmax]
-void smooth(glims_ctx* c, Amg* amg, Level& l, const double* b, double* x, bool zero_guess) {
+void smooth(glims_ctx* c, Amg* amg, Level& l, const double* b, double* x, bool zero_guess, bool fine) {
     const double lmax = l.lmax, lmin = amg->cheb_ratio * lmax;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
     double rho = 1.0 / sigma;
@@ -364,6 +364,7 @@ void smooth(glims_ctx* c, Amg* amg, Level& l, const double* b, double* x, bool z
         if (k == 0 && zero_guess) {
             GL_CUDA(cudaMemcpyAsync(l.r, b, sizeof(double) * (i64)l.n * l.bs, cudaMemcpyDeviceToDevice, c->stream));
         } else {
+            if (fine) halo_exchange(c, x, l.bs);      // partitioned mesh: the fine-level smoother is the global one
             launch_spmv_generic(c, l.pat, l.A, l.bs, x, l.r, b);
         }
         double c1, c2;
@@ -391,9 +392,10 @@ void vcycle(glims_ctx* c, Amg* amg, int li, const double* b, double* x) {
     }
     Level& lc = amg->L[li + 1];
     launch_zero(c, x, (i64)l.n * l.bs);
-    smooth(c, amg, l, b, x, true);
-    launch_spmv_generic(c, l.pat, l.A, l.bs, x, l.r, b);
     const bool l0 = (li == 0);
+    smooth(c, amg, l, b, x, true, l0);
+    if (l0) halo_exchange(c, x, l.bs);
+    launch_spmv_generic(c, l.pat, l.A, l.bs, x, l.r, b);
     if (D == 2) k_restrict<2><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r, lc.b);
     else k_restrict<3><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r, lc.b);
     c->launches++;
@@ -401,7 +403,7 @@ void vcycle(glims_ctx* c, Amg* amg, int li, const double* b, double* x) {
     if (D == 2) k_prolong_add<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x, x);
     else k_prolong_add<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x, x);
     c->launches++;
-    smooth(c, amg, l, b, x, false);
+    smooth(c, amg, l, b, x, false, l0);
 }
 
 void free_level(Level& l) {
