@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=148, help="voxel grid of the C4 ellipsoid (148 -> 10.19M tets)")
-    ap.add_argument("--pc", default="amg", choices=["amg", "jacobi"])
+    ap.add_argument("--pc", default="amg", choices=["amg", "amg64", "jacobi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
@@ -193,7 +193,7 @@ def main():
     else:
         eng = W.build_engine(w, device=local_rank)
         part = None
-    opts = dict(pc=N.PC_AMG if args.pc == "amg" else N.PC_JACOBI)
+    opts = dict(pc={"amg": N.PC_AMG, "amg64": N.PC_AMG_FP64, "jacobi": N.PC_JACOBI}[args.pc])
 
     def local_vec(x):
         return x if part is None else part.to_local(x)

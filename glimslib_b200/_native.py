@@ -24,7 +24,7 @@ SYMBOLS = [
 OK, ERR_ARG, ERR_CUDA, ERR_NOT_CONVERGED, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5
 ASM_RESIDUAL, ASM_KCONST, ASM_KCC, ASM_JACOBIAN, ASM_ALL = 1, 2, 4, 6, 7
 SOLVER_BLOCK_TRI, SOLVER_MONO_GMRES = 0, 1
-PC_JACOBI, PC_AMG = 0, 1
+PC_JACOBI, PC_AMG, PC_AMG_FP64 = 0, 1, 2
 ASMK_ATOMIC, ASMK_GATHER = 0, 1
 
 
@@ -32,7 +32,7 @@ class SolverOpts(C.Structure):
     _fields_ = [("snes_rtol", C.c_double), ("snes_atol", C.c_double), ("snes_stol", C.c_double),
                 ("max_newton", C.c_int32), ("ksp_rtol", C.c_double), ("ksp_atol", C.c_double),
                 ("max_krylov", C.c_int32), ("solver", C.c_int32), ("pc", C.c_int32),
-                ("asm_kernel", C.c_int32), ("lag_mechanics", C.c_int32)]
+                ("asm_kernel", C.c_int32), ("lag_mechanics", C.c_int32), ("recycle", C.c_int32)]
 
 
 class StepStats(C.Structure):

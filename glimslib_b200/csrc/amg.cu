@@ -38,6 +38,8 @@ struct Level {
     double* X = nullptr;        // [n][dim] node positions
     // work vectors
     double *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
+    // FP32 copies for the mixed-precision V-cycle (the outer PCG stays FP64)
+    float *A32 = nullptr, *dinv32 = nullptr, *x32 = nullptr, *b32 = nullptr, *r32 = nullptr, *d32 = nullptr;
 };
 
 }  // namespace
@@ -46,6 +48,7 @@ struct Amg {
     int dim = 0;
     std::vector<Level> L;
     double* coarse_inv = nullptr;
+    float* coarse_inv32 = nullptr;
     int coarse_m = 0;
     int cheb_degree = 2;
     double cheb_ratio = 0.1;
@@ -406,11 +409,265 @@ void vcycle(glims_ctx* c, Amg* amg, int li, const double* b, double* x) {
     smooth(c, amg, l, b, x, false, l0);
 }
 
+
+// ================================================================================================
+// Mixed-precision V-cycle: matrices, block-diagonal inverses and level vectors in FP32 (half the bytes of
+// the bandwidth-bound smoother), applied as a fixed linear preconditioner inside the FP64 PCG.
+__global__ void k_to_float(const double* __restrict__ a, float* __restrict__ b, i64 n) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) b[i] = (float)a[i];
+}
+__global__ void k_to_double(const float* __restrict__ a, double* __restrict__ b, i64 n) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) b[i] = (double)a[i];
+}
+
+// thread per block row (fine level, BS = 2|3): y = A x  or  y = rhs - A x
+template <int BS, bool RESID>
+__global__ void __launch_bounds__(TPB)
+k_spmv32_row(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+             const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ y, int n_rows,
+             const float* __restrict__ rhs) {
+    const int n_tiles = (n_rows + TPB - 1) / TPB;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int r = tile * TPB + threadIdx.x;
+        const int S = r >> 5, lane = r & 31;
+        if (S * 32 >= n_rows) continue;
+        float acc[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) acc[i] = 0.f;
+        const i64 base = slice_off[S];
+        const int w = slice_w[S];
+        for (int j = 0; j < w; ++j) {
+            const i64 g = base + (i64)j * 32;
+            const int cidx = __ldg(&col[g + lane]);
+            float xv[BS];
+#pragma unroll
+            for (int b = 0; b < BS; ++b) xv[b] = __ldg(&x[(i64)cidx * BS + b]);
+            const float* Ag = A + g * (BS * BS) + lane;
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+                for (int b = 0; b < BS; ++b) acc[i] += __ldcs(&Ag[(i * BS + b) * 32]) * xv[b];
+        }
+        if (r < n_rows) {
+#pragma unroll
+            for (int i = 0; i < BS; ++i) y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - acc[i] : acc[i];
+        }
+    }
+}
+
+// CTA per slice, warp per block-row component (coarse levels, BS = 3|6)
+template <int BS, bool RESID>
+__global__ void __launch_bounds__(32 * BS)
+k_spmv32_split(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+               const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ y, int n_rows,
+               int n_slices, const float* __restrict__ rhs) {
+    const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
+    for (int S = blockIdx.x; S < n_slices; S += gridDim.x) {
+        const int r = S * 32 + lane;
+        const i64 base = slice_off[S];
+        const int w = slice_w[S];
+        float acc0 = 0.f, acc1 = 0.f;
+        int j = 0;
+        for (; j + 1 < w; j += 2) {
+            const i64 g0 = base + (i64)j * 32, g1 = g0 + 32;
+            const int c0 = __ldg(&col[g0 + lane]), c1 = __ldg(&col[g1 + lane]);
+            const float* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+            const float* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < BS; ++b) {
+                acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+                acc1 += __ldcs(&A1[b * 32]) * __ldg(&x[(i64)c1 * BS + b]);
+            }
+        }
+        if (j < w) {
+            const i64 g0 = base + (i64)j * 32;
+            const int c0 = __ldg(&col[g0 + lane]);
+            const float* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+        }
+        if (r < n_rows) {
+            const float v = acc0 + acc1;
+            y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - v : v;
+        }
+    }
+}
+
+template <int BS>
+__global__ void k_cheb_update32(const float* __restrict__ dinv, const float* __restrict__ r, float* __restrict__ d,
+                                float* __restrict__ x, int n, float c1, float c2) {
+    for (i64 row = blockIdx.x * (i64)TPB + threadIdx.x; row < n; row += (i64)gridDim.x * TPB) {
+        float rv[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) rv[i] = r[row * BS + i];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            float z = 0.f;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) z += dinv[row * BS * BS + i * BS + j] * rv[j];
+            float dn = c2 * z + (c1 != 0.f ? c1 * d[row * BS + i] : 0.f);
+            d[row * BS + i] = dn;
+            x[row * BS + i] += dn;
+        }
+    }
+}
+
+template <int D>
+__global__ void k_restrict32(int nc, const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx, bool level0,
+                             const double* __restrict__ rvec, const unsigned char* __restrict__ free_mask,
+                             const float* __restrict__ rf, float* __restrict__ rc) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nc) return;
+    constexpr int NR = (D == 2) ? 1 : 3;
+    const int bsc = D + NR, bsf = level0 ? D : bsc;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int m = mem_ptr[I]; m < mem_ptr[I + 1]; ++m) {
+        const int i = mem_idx[m];
+        double P[6][6];
+        int a_, b_;
+        build_P<D>(level0, rvec + (i64)i * D, level0 ? free_mask[i] : 0xffu, P, a_, b_);
+        for (int k = 0; k < bsf; ++k) {
+            double v = rf[(i64)i * bsf + k];
+            for (int j = 0; j < bsc; ++j) acc[j] += P[k][j] * v;
+        }
+    }
+    for (int j = 0; j < bsc; ++j) rc[(i64)I * bsc + j] = (float)acc[j];
+}
+
+template <int D>
+__global__ void k_prolong_add32(int n, const int* __restrict__ agg, bool level0, const double* __restrict__ rvec,
+                                const unsigned char* __restrict__ free_mask, const float* __restrict__ xc,
+                                float* __restrict__ xf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int I = agg[i];
+    if (I < 0) return;
+    constexpr int NR = (D == 2) ? 1 : 3;
+    const int bsc = D + NR, bsf = level0 ? D : bsc;
+    double P[6][6];
+    int a_, b_;
+    build_P<D>(level0, rvec + (i64)i * D, level0 ? free_mask[i] : 0xffu, P, a_, b_);
+    for (int k = 0; k < bsf; ++k) {
+        double v = 0;
+        for (int j = 0; j < bsc; ++j) v += P[k][j] * (double)xc[(i64)I * bsc + j];
+        xf[(i64)i * bsf + k] += (float)v;
+    }
+}
+
+__global__ void k_dense_matvec32(const float* __restrict__ M, const float* __restrict__ x, float* __restrict__ y, int m) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= m) return;
+    float s = 0.f;
+    for (int j = lane; j < m; j += 32) s += M[(i64)row * m + j] * x[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+}
+
+inline int sgrid(i64 n) { i64 g = (n + TPB - 1) / TPB; return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g)); }
+
+void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) {
+    const SellPattern& p = l.pat;
+    if (l.owns_A) {      // coarse levels (6x6 blocks in 3D, 3x3 in 2D): few rows, use the split kernel
+        int g = p.n_slices < 148 * 16 ? p.n_slices : 148 * 16;
+        if (g < 1) g = 1;
+        if (l.bs == 6) {
+            if (rhs) k_spmv32_split<6, true><<<g, 192, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, p.n_slices, rhs);
+            else k_spmv32_split<6, false><<<g, 192, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, p.n_slices, nullptr);
+        } else {
+            if (rhs) k_spmv32_split<3, true><<<g, 96, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, p.n_slices, rhs);
+            else k_spmv32_split<3, false><<<g, 96, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, p.n_slices, nullptr);
+        }
+    } else {
+        int g = sgrid(p.n_rows);
+        if (l.bs == 2) {
+            if (rhs) k_spmv32_row<2, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, rhs);
+            else k_spmv32_row<2, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, nullptr);
+        } else {
+            if (rhs) k_spmv32_row<3, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, rhs);
+            else k_spmv32_row<3, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, nullptr);
+        }
+    }
+    c->launches++;
+}
+
+void smooth32(glims_ctx* c, Amg* amg, Level& l, const float* b, float* x, bool zero_guess, bool fine) {
+    const double lmax = l.lmax, lmin = amg->cheb_ratio * lmax;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    for (int k = 0; k < amg->cheb_degree; ++k) {
+        if (k == 0 && zero_guess) {
+            GL_CUDA(cudaMemcpyAsync(l.r32, b, sizeof(float) * (i64)l.n * l.bs, cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            if (fine) halo_exchange_f32(c, x, l.bs);
+            spmv32(c, l, x, l.r32, b);
+        }
+        double c1, c2;
+        if (k == 0) { c1 = 0.0; c2 = 1.0 / theta; }
+        else {
+            double rho_new = 1.0 / (2.0 * sigma - rho);
+            c1 = rho_new * rho;
+            c2 = 2.0 * rho_new / delta;
+            rho = rho_new;
+        }
+        int g = sgrid(l.n);
+        if (l.bs == 2) k_cheb_update32<2><<<g, TPB, 0, c->stream>>>(l.dinv32, l.r32, l.d32, x, l.n, (float)c1, (float)c2);
+        else if (l.bs == 3) k_cheb_update32<3><<<g, TPB, 0, c->stream>>>(l.dinv32, l.r32, l.d32, x, l.n, (float)c1, (float)c2);
+        else k_cheb_update32<6><<<g, TPB, 0, c->stream>>>(l.dinv32, l.r32, l.d32, x, l.n, (float)c1, (float)c2);
+        c->launches++;
+    }
+}
+
+void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
+    Level& l = amg->L[li];
+    const int D = amg->dim;
+    if (li == (int)amg->L.size() - 1) {
+        int m = amg->coarse_m;
+        k_dense_matvec32<<<(m + 7) / 8, 256, 0, c->stream>>>(amg->coarse_inv32, b, x, m);
+        c->launches++;
+        return;
+    }
+    Level& lc = amg->L[li + 1];
+    const bool l0 = (li == 0);
+    GL_CUDA(cudaMemsetAsync(x, 0, sizeof(float) * (i64)l.n * l.bs, c->stream));
+    smooth32(c, amg, l, b, x, true, l0);
+    if (l0) halo_exchange_f32(c, x, l.bs);
+    spmv32(c, l, x, l.r32, b);
+    if (D == 2) k_restrict32<2><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
+    else k_restrict32<3><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
+    c->launches++;
+    vcycle32(c, amg, li + 1, lc.b32, lc.x32);
+    if (D == 2) k_prolong_add32<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, x);
+    else k_prolong_add32<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, x);
+    c->launches++;
+    smooth32(c, amg, l, b, x, false, l0);
+}
+
+void build_fp32(glims_ctx* c, Amg* amg) {
+    for (auto& l : amg->L) {
+        i64 na = l.pat.n_slots * l.bs * l.bs, nd = (i64)l.n * l.bs * l.bs, nv = std::max<i64>(l.n_cols, l.n) * l.bs;
+        GL_CUDA(cudaMalloc(&l.A32, sizeof(float) * std::max<i64>(na, 1)));
+        GL_CUDA(cudaMalloc(&l.dinv32, sizeof(float) * std::max<i64>(nd, 1)));
+        k_to_float<<<sgrid(na), TPB, 0, c->stream>>>(l.A, l.A32, na);
+        k_to_float<<<sgrid(nd), TPB, 0, c->stream>>>(l.dinv, l.dinv32, nd);
+        for (float** v : {&l.x32, &l.b32, &l.r32, &l.d32}) {
+            GL_CUDA(cudaMalloc(v, sizeof(float) * std::max<i64>(nv, 1)));
+            GL_CUDA(cudaMemsetAsync(*v, 0, sizeof(float) * std::max<i64>(nv, 1), c->stream));
+        }
+    }
+    i64 m2 = (i64)amg->coarse_m * amg->coarse_m;
+    GL_CUDA(cudaMalloc(&amg->coarse_inv32, sizeof(float) * std::max<i64>(m2, 1)));
+    k_to_float<<<sgrid(m2), TPB, 0, c->stream>>>(amg->coarse_inv, amg->coarse_inv32, m2);
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+}
+
 void free_level(Level& l) {
     if (l.owns_pat) free_pattern(l.pat);
     if (l.owns_A && l.A) cudaFree(l.A);
     for (void* q : {(void*)l.dinv, (void*)l.agg, (void*)l.rvec, (void*)l.free_mask, (void*)l.mem_ptr, (void*)l.mem_idx,
-                    (void*)l.X, (void*)l.x, (void*)l.b, (void*)l.r, (void*)l.d})
+                    (void*)l.X, (void*)l.x, (void*)l.b, (void*)l.r, (void*)l.d, (void*)l.A32, (void*)l.dinv32,
+                    (void*)l.x32, (void*)l.b32, (void*)l.r32, (void*)l.d32})
         if (q) cudaFree(q);
 }
 
@@ -420,6 +677,7 @@ void amg_free(glims_ctx* c) {
     if (!c->amg) return;
     for (auto& l : c->amg->L) free_level(l);
     if (c->amg->coarse_inv) cudaFree(c->amg->coarse_inv);
+    if (c->amg->coarse_inv32) cudaFree(c->amg->coarse_inv32);
     delete c->amg;
     c->amg = nullptr;
 }
@@ -549,14 +807,25 @@ void amg_setup(glims_ctx* c) {
     // ---- smoother spectra ----------------------------------------------------------------------------
     for (size_t li = 0; li + 1 < amg->L.size(); ++li) estimate_lmax(c, amg->L[li]);
     GL_CUDA(cudaStreamSynchronize(c->stream));
+    build_fp32(c, amg);
 }
 
-void amg_vcycle(glims_ctx* c, const double* r, double* z) {
+void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32) {
     Amg* amg = c->amg;
-    if (amg->L.size() == 1) {     // tiny problem: the dense inverse is the whole hierarchy
-        k_dense_matvec<<<(amg->coarse_m + 7) / 8, 256, 0, c->stream>>>(amg->coarse_inv, r, z, amg->coarse_m);
-        c->launches++;
+    if (!fp32) {
+        if (amg->L.size() == 1) {     // tiny problem: the dense inverse is the whole hierarchy
+            k_dense_matvec<<<(amg->coarse_m + 7) / 8, 256, 0, c->stream>>>(amg->coarse_inv, r, z, amg->coarse_m);
+            c->launches++;
+            return;
+        }
+        vcycle(c, amg, 0, r, z);
         return;
     }
-    vcycle(c, amg, 0, r, z);
+    Level& l0 = amg->L[0];
+    const i64 n = (i64)l0.n * l0.bs;
+    k_to_float<<<sgrid(n), TPB, 0, c->stream>>>(r, l0.b32, n);
+    if (amg->L.size() == 1) k_dense_matvec32<<<(amg->coarse_m + 7) / 8, 256, 0, c->stream>>>(amg->coarse_inv32, l0.b32, l0.x32, amg->coarse_m);
+    else vcycle32(c, amg, 0, l0.b32, l0.x32);
+    k_to_double<<<sgrid(n), TPB, 0, c->stream>>>(l0.x32, z, n);
+    c->launches += 3;
 }

@@ -40,6 +40,34 @@ void halo_exchange(glims_ctx* c, double* xb, int bs) {
     GL_NCCL(ncclGroupEnd());
 }
 
+namespace {
+__global__ void k_pack32(const float* __restrict__ x, const int* __restrict__ idx, i64 n, int bs, float* buf) {
+    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (t >= n * bs) return;
+    i64 v = t / bs; int k = (int)(t - v * bs);
+    buf[t] = x[(i64)idx[v] * bs + k];
+}
+}  // namespace
+
+void halo_exchange_f32(glims_ctx* c, float* xb, int bs) {
+    Halo& h = c->halo;
+    if (!h.active || !h.comm) return;
+    ncclComm_t comm = (ncclComm_t)h.comm;
+    float* sb = (float*)h.send_buf;
+    if (h.n_send > 0) {
+        i64 n = h.n_send * bs;
+        k_pack32<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(xb, h.send_idx, h.n_send, bs, sb);
+        c->launches++;
+    }
+    GL_NCCL(ncclGroupStart());
+    for (size_t p = 0; p < h.peers.size(); ++p) {
+        i64 ns = h.send_ptr[p + 1] - h.send_ptr[p], nr = h.recv_ptr[p + 1] - h.recv_ptr[p];
+        if (ns > 0) GL_NCCL(ncclSend(sb + h.send_ptr[p] * bs, ns * bs, ncclFloat, h.peers[p], comm, c->stream));
+        if (nr > 0) GL_NCCL(ncclRecv(xb + (h.n_owned + h.recv_ptr[p]) * bs, nr * bs, ncclFloat, h.peers[p], comm, c->stream));
+    }
+    GL_NCCL(ncclGroupEnd());
+}
+
 void allreduce_scalars(glims_ctx* c, int slot0, int n) {
     Halo& h = c->halo;
     if (!h.active || !h.comm) return;

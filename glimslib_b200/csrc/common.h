@@ -119,6 +119,8 @@ struct glims_ctx {
     Amg* amg = nullptr;
     Halo halo;
     bool first_step_done = false;
+    // successive-right-hand-side projection for the constant K_uu (solver.cu: pcg)
+    int rec_n = 0, rec_head = 0;
 };
 
 // ---------------- pattern.cu
@@ -176,8 +178,9 @@ void flush_l2(glims_ctx* c);
 // ---------------- amg.cu
 void amg_setup(glims_ctx* c);
 void amg_free(glims_ctx* c);
-void amg_vcycle(glims_ctx* c, const double* r, double* z);   // z = M^-1 r on K_uu ([n_v][dim] vectors)
+void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32);   // z = M^-1 r on K_uu ([n_v][dim] vectors)
 
 // ---------------- comm.cu
 void halo_exchange(glims_ctx* c, double* xb, int bs);        // fill ghost values of a blocked vector
+void halo_exchange_f32(glims_ctx* c, float* xb, int bs);
 void allreduce_scalars(glims_ctx* c, int slot0, int n);      // in-place sum over ranks of c->scal slots

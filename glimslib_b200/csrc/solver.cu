@@ -61,8 +61,8 @@ i64 nrows(glims_ctx* c) { return c->pat.n_rows; }
 void apply_pc(glims_ctx* c, int which, int pc, const double* r, double* z, int s_rz) {
     if (which == 2) { launch_block_jacobi(c, c->dinv_cc, 1, r, z, nrows(c), s_rz); return; }
     if (which == 1) {
-        if (pc == GLIMS_PC_AMG && c->amg) {
-            amg_vcycle(c, r, z);
+        if ((pc == GLIMS_PC_AMG || pc == GLIMS_PC_AMG_FP64) && c->amg) {
+            amg_vcycle(c, r, z, pc == GLIMS_PC_AMG);
             launch_dot(c, r, z, nrows(c) * c->dim, s_rz);
         } else launch_block_jacobi(c, c->dinv_uu, c->dim, r, z, nrows(c), s_rz);
         return;
@@ -71,8 +71,10 @@ void apply_pc(glims_ctx* c, int which, int pc, const double* r, double* z, int s
 }
 
 // PCG on block `which` (1: K_uu, 2: K_cc), zero initial guess. Returns iterations, or -1 if not converged.
+constexpr int REC_M = 8;     // directions kept for the successive-RHS projection
+
 int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_rel, double scale, double tol_abs,
-        int maxit, double* res_out) {
+        int maxit, double* res_out, bool recycle = false) {
     const int bs = which == 1 ? c->dim : 1;
     const i64 n = nrows(c) * bs, nl = c->n_v * bs;
     const char* tag = which == 1 ? "u" : "c";
@@ -81,15 +83,41 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
     double *r = W("r"), *p = W("p"), *Ap = W("Ap"), *z = W("z");
     launch_copy(c, b, r, n);
     launch_zero(c, x, n);
+    // Successive right-hand sides, same SPD matrix (K_uu is constant over Newton iterations and time steps):
+    // Galerkin-project b onto the A-orthonormal corrections U of earlier solves (Fischer 1998), then let PCG
+    // solve only for the remainder.  x_bar = U (U^T b), r0 = b - (A U)(U^T b).
+    double *U = nullptr, *AU = nullptr, *r0 = nullptr, *coef = nullptr;
+    recycle = recycle && which == 1;
+    if (recycle) {
+        U = ws(c, "rec_U", nl * REC_M); AU = ws(c, "rec_AU", nl * REC_M);
+        r0 = ws(c, "rec_r0", nl); coef = ws(c, "rec_coef", 64);
+        if (c->rec_n > 0) {
+            launch_multi_dot(c, U, nl, c->rec_n, b, n, S_GM0);
+            allreduce_scalars(c, S_GM0, c->rec_n);
+            GL_CUDA(cudaMemcpyAsync(coef, c->scal + S_GM0, sizeof(double) * c->rec_n, cudaMemcpyDeviceToDevice, c->stream));
+            launch_multi_axpy(c, U, nl, c->rec_n, coef, 1.0, x, n);
+            launch_multi_axpy(c, AU, nl, c->rec_n, coef, -1.0, r, n);
+        }
+        launch_copy(c, r, r0, n);
+    }
     launch_dot(c, b, b, n, S_BN);
+    launch_dot(c, r, r, n, S_TMP3);
     allreduce_scalars(c, S_BN, 1);
-    double bn2;
+    allreduce_scalars(c, S_TMP3, 1);
+    double bn2, rn2;
     read_scalars(c, S_BN, 1, &bn2);
-    double bn = std::sqrt(bn2);
+    read_scalars(c, S_TMP3, 1, &rn2);
+    double bn = std::sqrt(bn2), rn0 = std::sqrt(rn2);
     if (scale <= 0) scale = bn;
     double tol = std::max(tol_rel * scale, tol_abs);
-    if (res_out) *res_out = bn;
-    if (bn <= tol || bn == 0.0) return 0;
+    if (res_out) *res_out = rn0;
+    if (rn0 <= tol || bn == 0.0) return 0;
+    double* xbar = nullptr;
+    if (recycle) {      // PCG iterates on the correction only; keep x_bar aside
+        xbar = ws(c, "rec_xbar", nl);
+        launch_copy(c, x, xbar, n);
+        launch_zero(c, x, n);
+    }
     int cur = S_RZ, nxt = S_RZNEW;
     apply_pc(c, which, pc, r, z, cur);
     allreduce_scalars(c, cur, 1);
@@ -123,6 +151,38 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
         }
     }
     cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    if (recycle) {
+        if (result >= 0) {
+            // new direction w = correction, A w = r0 - r_final; A-orthonormalise against the kept ones, append
+            double* Aw = r0;
+            launch_axpy(c, -1.0, r, Aw, n);
+            const int slot = c->rec_head;
+            double *Un = U + (i64)slot * nl, *AUn = AU + (i64)slot * nl;
+            // (the slot being overwritten is excluded from the projection: project against the other kept ones)
+            launch_copy(c, x, Un, n);
+            launch_copy(c, Aw, AUn, n);
+            for (int k = 0; k < c->rec_n; ++k) {
+                if (k == slot) continue;
+                launch_dot(c, AU + (i64)k * nl, Un, n, S_TMP0);
+                allreduce_scalars(c, S_TMP0, 1);
+                double beta; read_scalars(c, S_TMP0, 1, &beta);
+                launch_axpy(c, -beta, U + (i64)k * nl, Un, n);
+                launch_axpy(c, -beta, AU + (i64)k * nl, AUn, n);
+            }
+            launch_dot(c, Un, AUn, n, S_TMP0);
+            allreduce_scalars(c, S_TMP0, 1);
+            double nn; read_scalars(c, S_TMP0, 1, &nn);
+            if (nn > 0 && nn == nn) {
+                launch_scale(c, 1.0 / std::sqrt(nn), Un, n);
+                launch_scale(c, 1.0 / std::sqrt(nn), AUn, n);
+                if (c->rec_n < REC_M) c->rec_n++;
+                c->rec_head = (slot + 1) % REC_M;
+            } else if (slot < c->rec_n) {     // degenerate direction: drop the slot we clobbered
+                c->rec_n = 0; c->rec_head = 0;
+            }
+        }
+        launch_axpy(c, 1.0, xbar, x, n);      // x = x_bar + correction
+    }
     return result;
 }
 
@@ -216,12 +276,13 @@ int gmres_mono(glims_ctx* c, const double* b, double* x, double tol, int maxit, 
 }
 
 void ensure_kconst(glims_ctx* c, const glims_solver_opts* o) {
-    bool need_amg = (o->pc == GLIMS_PC_AMG) && o->solver == GLIMS_SOLVER_BLOCK_TRI;
+    bool need_amg = (o->pc == GLIMS_PC_AMG || o->pc == GLIMS_PC_AMG_FP64) && o->solver == GLIMS_SOLVER_BLOCK_TRI;
     if (!c->kconst_valid) {
         launch_assemble(c, GLIMS_ASM_KCONST, o->asm_kernel);
         launch_bc_matrix(c, GLIMS_ASM_KCONST, true);
         launch_diag_inverse(c, 1);
         c->kconst_valid = true;
+        c->rec_n = c->rec_head = 0;
         if (c->amg) amg_free(c);
     }
     if (need_amg && !c->amg) amg_setup(c);
@@ -308,7 +369,7 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
                 }
                 launch_scale(c, -1.0, Fu, nr * D);
                 double res = 0;
-                int its = pcg(c, 1, o->pc, Fu, du, o->ksp_rtol, fu_scale, o->ksp_atol, o->max_krylov, &res);
+                int its = pcg(c, 1, o->pc, Fu, du, o->ksp_rtol, fu_scale, o->ksp_atol, o->max_krylov, &res, o->recycle != 0);
                 if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "PCG on K_uu did not converge");
                 s.krylov_its_u += its;
                 launch_insert_add(c, c->x, du, dc, 1.0);
@@ -338,6 +399,7 @@ void glims_default_opts(glims_solver_opts* o) {
     o->ksp_rtol = 1e-10; o->ksp_atol = 1e-300; o->max_krylov = 20000;
     o->solver = GLIMS_SOLVER_BLOCK_TRI; o->pc = GLIMS_PC_AMG; o->asm_kernel = GLIMS_ASMK_ATOMIC;
     o->lag_mechanics = 1;
+    o->recycle = 1;
 }
 
 int glims_create(glims_ctx** out, int32_t dim, int64_t n_vertices, const double* coords, int64_t n_cells,

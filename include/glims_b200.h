@@ -44,7 +44,9 @@ enum { GLIMS_ASM_RESIDUAL = 1, GLIMS_ASM_KCONST = 2 /* K_uu, K_uc */, GLIMS_ASM_
 enum { GLIMS_SOLVER_BLOCK_TRI = 0,   /* exact block back-substitution of J = [[K_uu,K_uc],[0,K_cc]]: PCG on each block */
        GLIMS_SOLVER_MONO_GMRES = 1   /* GMRES(30) on the monolithic J, block-Jacobi left PC (PETSc-default-like) */ };
 enum { GLIMS_PC_JACOBI = 0,          /* (block-)Jacobi on every block */
-       GLIMS_PC_AMG = 1              /* aggregation AMG V-cycle on K_uu, Jacobi on K_cc */ };
+       GLIMS_PC_AMG = 1,             /* aggregation AMG V-cycle on K_uu (FP32 storage inside the V-cycle,
+                                        FP64 outer PCG), Jacobi on K_cc */
+       GLIMS_PC_AMG_FP64 = 2         /* same hierarchy, V-cycle entirely in FP64 */ };
 /* assembly kernel variant for the Jacobian */
 enum { GLIMS_ASMK_ATOMIC = 0,        /* element-parallel, scatter map + RED.ADD.F64 */
        GLIMS_ASMK_GATHER = 1         /* row-parallel gather through the transposed scatter map: no atomics, deterministic */ };
@@ -64,6 +66,8 @@ typedef struct {
     int32_t asm_kernel;      /* GLIMS_ASMK_* */
     int32_t lag_mechanics;   /* 1: skip the K_uu solve until the concentration block has converged
                                 (same fixed point; the displacement does not feed back, stg:110-120) */
+    int32_t recycle;         /* 1: project every K_uu solve onto the A-orthonormalised corrections of the previous
+                                (up to 8) solves before PCG starts -- K_uu is constant, the loads vary smoothly in time */
 } glims_solver_opts;
 
 typedef struct {

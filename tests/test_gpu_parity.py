@@ -138,7 +138,7 @@ def c1_problem(nx=50):
     return prob, x0
 
 
-@pytest.mark.parametrize("mode", ["block_tri_jacobi", "block_tri_amg", "block_tri_nolag", "mono_gmres"])
+@pytest.mark.parametrize("mode", ["block_tri_jacobi", "block_tri_amg", "block_tri_amg_fp64", "block_tri_nolag", "mono_gmres"])
 def test_c1_time_loop_matches_oracle(mode):
     """Config C1, 10 backward-Euler steps: each step's field within 1e-8 relative L2 of the oracle
     (oracle: Newton + sparse LU to rtol 1e-12).  The device solve runs SNES rtol 1e-10 / KSP rtol 1e-12."""
@@ -153,7 +153,9 @@ def test_c1_time_loop_matches_oracle(mode):
     elif mode == "block_tri_jacobi":
         kw.update(solver=0, pc=0)
     elif mode == "block_tri_amg":
-        kw.update(solver=0, pc=1)
+        kw.update(solver=0, pc=1)          # FP32-storage V-cycle inside FP64 PCG
+    elif mode == "block_tri_amg_fp64":
+        kw.update(solver=0, pc=2)
     else:
         kw.update(solver=0, pc=0, lag_mechanics=0)
     nb = 3
