@@ -25,7 +25,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NOT_CONVERGED, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -
 ASM_RESIDUAL, ASM_KCONST, ASM_KCC, ASM_JACOBIAN, ASM_ALL = 1, 2, 4, 6, 7
 SOLVER_BLOCK_TRI, SOLVER_MONO_GMRES = 0, 1
 PC_JACOBI, PC_AMG, PC_AMG_FP64 = 0, 1, 2
-ASMK_ATOMIC, ASMK_GATHER = 0, 1
+ASMK_ATOMIC, ASMK_GATHER, ASMK_SLICE = 0, 1, 2
 
 
 class SolverOpts(C.Structure):

@@ -88,6 +88,13 @@ struct glims_ctx {
     i64* gptr = nullptr;        // [n_slots+1]
     int* gent = nullptr;        // [n_c*nb*nb] packed: element<<4 | a<<2 | b
     bool have_gather = false;
+    // slice-local assembly: per SELL slice the elements touching its rows + contributor entries against that list
+    i64* sl_ptr = nullptr;      // [n_slices+1]
+    int* sl_elem = nullptr;     // [sl_total]
+    unsigned short* lent = nullptr;   // [#contributors] (local element index << 4) | a << 2 | b
+    int sl_max = 0;
+    i64 sl_total = 0;
+    bool have_slice = false;
 
     // matrices (SELL value layout, see vidx)
     double *Kuu = nullptr, *Kuc = nullptr, *Kcc = nullptr;
@@ -126,6 +133,7 @@ struct glims_ctx {
 // ---------------- pattern.cu
 void build_pattern(glims_ctx* c);
 void build_gather_map(glims_ctx* c);
+void build_slice_map(glims_ctx* c);
 // SELL pattern from unsorted 64-bit (row<<32|col) keys on the device; ~0 keys are dropped. keys is consumed.
 // ukeys_out (optional) receives the sorted unique keys (device, caller frees), in CSR order.
 void build_pattern_from_keys(cudaStream_t st, unsigned long long* keys, i64 n_keys, i64 n_rows, SellPattern& P,

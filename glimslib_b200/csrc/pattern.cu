@@ -12,6 +12,8 @@
 #include <thrust/iterator/transform_iterator.h>
 #include <thrust/reduce.h>
 #include <thrust/extrema.h>
+#include <algorithm>
+#include <vector>
 
 namespace {
 
@@ -109,6 +111,37 @@ __global__ void k_gather_unpack(const unsigned long long* __restrict__ keys, i64
     int ab = (int)(p - (unsigned long long)e * nbnb);
     int a = ab / nb, b = ab - a * nb;
     gent[t] = (int)((e << 4) | (a << 2) | b);
+}
+
+// ---- slice-local assembly maps ---------------------------------------------------------------------
+__global__ void k_slice_elem_keys(const int* __restrict__ cells, i64 n_c, int nb, i64 n_own, unsigned long long* keys) {
+    i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (p >= n_c * nb) return;
+    i64 e = p / nb;
+    int v = cells[p];
+    keys[p] = (v < n_own) ? (((unsigned long long)(v >> 5) << 32) | (unsigned long long)e) : ~0ULL;
+}
+struct SliceStart {
+    __host__ __device__ unsigned long long operator()(i64 S) const { return (unsigned long long)S << 32; }
+};
+__global__ void k_slice_elem_unpack(const unsigned long long* __restrict__ keys, i64 n, int* out) {
+    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = (int)(keys[t] & 0xffffffffu);
+}
+// contributor entries re-expressed with the element's index inside its slice's element list
+__global__ void k_local_entries(const i64* __restrict__ slice_off, const i64* __restrict__ gptr,
+                                const int* __restrict__ gent, const i64* __restrict__ sl_ptr,
+                                const int* __restrict__ sl_elem, unsigned short* __restrict__ lent) {
+    const int S = blockIdx.x;
+    const i64 t0 = gptr[slice_off[S]], t1 = gptr[slice_off[S + 1]];
+    const i64 p0 = sl_ptr[S], p1 = sl_ptr[S + 1];
+    for (i64 t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const int ent = gent[t];
+        const int e = ent >> 4;
+        i64 lo = p0, hi = p1;
+        while (lo < hi) { i64 mid = (lo + hi) >> 1; if (sl_elem[mid] < e) lo = mid + 1; else hi = mid; }
+        lent[t] = (unsigned short)(((lo - p0) << 4) | (ent & 15));
+    }
 }
 
 struct SlotStart {
@@ -209,4 +242,49 @@ void build_gather_map(glims_ctx* c) {
     k_gather_unpack<<<nblk(nvalid), 256, 0, c->stream>>>(kp, nvalid, nb * nb, nb, c->gent);
     GL_CUDA(cudaStreamSynchronize(c->stream));
     c->have_gather = true;
+}
+
+// Per SELL slice: the sorted list of elements touching one of its 32 rows, and the contributor entries of the
+// gather map rewritten against that list (12-bit local element index | a | b) for the slice-local kernel.
+void build_slice_map(glims_ctx* c) {
+    if (c->have_slice) return;
+    build_gather_map(c);
+    auto pol = thrust::cuda::par.on(c->stream);
+    const int nb = c->nb;
+    const i64 n_own = c->pat.n_rows, np = c->n_c * nb;
+    const int n_slices = c->pat.n_slices;
+    thrust::device_vector<unsigned long long> keys(np);
+    unsigned long long* kp = thrust::raw_pointer_cast(keys.data());
+    k_slice_elem_keys<<<nblk(np), 256, 0, c->stream>>>(c->cells, c->n_c, nb, n_own, kp);
+    thrust::sort(pol, keys.begin(), keys.end());
+    auto uend = thrust::unique(pol, keys.begin(), keys.end());
+    i64 nu = uend - keys.begin();
+    if (nu > 0) {
+        unsigned long long last;
+        GL_CUDA(cudaMemcpyAsync(&last, kp + nu - 1, 8, cudaMemcpyDeviceToHost, c->stream));
+        GL_CUDA(cudaStreamSynchronize(c->stream));
+        if (last == ~0ULL) nu -= 1;
+    }
+    GL_CUDA(cudaMalloc(&c->sl_ptr, sizeof(i64) * (n_slices + 1)));
+    GL_CUDA(cudaMalloc(&c->sl_elem, sizeof(int) * (nu > 0 ? nu : 1)));
+    thrust::device_ptr<i64> sp(c->sl_ptr);
+    thrust::lower_bound(pol, keys.begin(), keys.begin() + nu,
+                        thrust::make_transform_iterator(thrust::counting_iterator<i64>(0), SliceStart()),
+                        thrust::make_transform_iterator(thrust::counting_iterator<i64>(n_slices + 1), SliceStart()), sp);
+    k_slice_elem_unpack<<<nblk(nu), 256, 0, c->stream>>>(kp, nu, c->sl_elem);
+    // largest element list decides the shared-memory footprint
+    std::vector<i64> h(n_slices + 1);
+    GL_CUDA(cudaMemcpyAsync(h.data(), c->sl_ptr, sizeof(i64) * (n_slices + 1), cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    i64 mx = 0;
+    for (int S = 0; S < n_slices; ++S) mx = std::max(mx, h[S + 1] - h[S]);
+    c->sl_max = (int)mx;
+    c->sl_total = nu;
+    i64 n_ent;
+    GL_CUDA(cudaMemcpy(&n_ent, c->gptr + c->pat.n_slots, sizeof(i64), cudaMemcpyDeviceToHost));
+    GL_CUDA(cudaMalloc(&c->lent, sizeof(unsigned short) * (n_ent > 0 ? n_ent : 1)));
+    if (mx < 4096)
+        k_local_entries<<<n_slices, 256, 0, c->stream>>>(c->pat.slice_off, c->gptr, c->gent, c->sl_ptr, c->sl_elem, c->lent);
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_slice = true;
 }

@@ -456,7 +456,7 @@ int glims_destroy(glims_ctx* c) {
                     (void*)c->gent, (void*)c->Kuu, (void*)c->Kuc, (void*)c->Kcc, (void*)c->dinv_uu, (void*)c->dinv_cc,
                     (void*)c->dinv_mono, (void*)c->x, (void*)c->xprev, (void*)c->F, (void*)c->fext, (void*)c->dx,
                     (void*)c->bc_dofs, (void*)c->bc_vals, (void*)c->bcmask, (void*)c->scal, (void*)c->partials,
-                    (void*)c->tickets, (void*)c->flush_buf, (void*)c->halo.send_idx, (void*)c->halo.send_buf})
+                    (void*)c->tickets, (void*)c->flush_buf, (void*)c->sl_ptr, (void*)c->sl_elem, (void*)c->lent, (void*)c->halo.send_idx, (void*)c->halo.send_buf})
         if (q) cudaFree(q);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->stream) cudaStreamDestroy(c->stream);

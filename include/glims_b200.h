@@ -49,7 +49,8 @@ enum { GLIMS_PC_JACOBI = 0,          /* (block-)Jacobi on every block */
        GLIMS_PC_AMG_FP64 = 2         /* same hierarchy, V-cycle entirely in FP64 */ };
 /* assembly kernel variant for the Jacobian */
 enum { GLIMS_ASMK_ATOMIC = 0,        /* element-parallel, scatter map + RED.ADD.F64 */
-       GLIMS_ASMK_GATHER = 1         /* row-parallel gather through the transposed scatter map: no atomics, deterministic */ };
+       GLIMS_ASMK_GATHER = 1,        /* row-parallel gather through the transposed scatter map: no atomics, deterministic */
+       GLIMS_ASMK_SLICE = 2          /* gather with the element geometry of each 32-row slice staged in shared memory */ };
 
 typedef struct {
     /* SNES-like controls; defaults mirror DOLFIN's PETScSNESSolver defaults that

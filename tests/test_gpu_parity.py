@@ -58,7 +58,7 @@ def relerr(a, b):
 
 
 @pytest.mark.parametrize("d", [2, 3])
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_assembly_matches_oracle(d, kernel):
     """K1/K2: residual and Jacobian values, raw and with DOLFIN-style Dirichlet rows; <= 1e-13 relative."""
     prob, rng = small_problem(d)
@@ -94,10 +94,11 @@ def test_atomic_and_gather_kernels_agree(d):
     eng.set_state(rng.standard_normal(prob.ndof))
     eng.assemble(what=6, kernel=0)
     a = eng.export_blocks()
-    eng.assemble(what=6, kernel=1)
-    b = eng.export_blocks()
-    for p, q in zip(a[2:], b[2:]):
-        assert relerr(p, q) < 1e-13
+    for kernel in (1, 2):
+        eng.assemble(what=6, kernel=kernel)
+        b = eng.export_blocks()
+        for p, q in zip(a[2:], b[2:]):
+            assert relerr(p, q) < 1e-13
     eng.close()
 
 
