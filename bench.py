@@ -284,7 +284,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "n_tets": int(w["mesh"].num_cells()),
                        "n_vertices": int(w["mesh"].num_vertices()), "n_dofs": int(w["mesh"].num_vertices() * 4),
-                       "nnz_blocks": int(eng.nnzb), "dt": w["dt"], "solver": "block-triangular Newton-PCG, pc=%s" % args.pc,
+                       "nnz_blocks": int(eng.nnzb), "dt": w["dt"], "solver": "block-triangular Newton-PCG, pc=%s (aggregation AMG, FP32-storage V-cycle) + successive-RHS projection" % args.pc,
                        "tolerances": "SNES rtol 1e-9 atol 1e-10 (monolithic |F|), KSP rtol 1e-10",
                        "timing": "inputs larger than L2 (matrix 1.9 GB, vectors 42-56 MB); wall clock between "
                                  "device syncs, max over ranks",
@@ -294,6 +294,7 @@ def main():
                        "krylov_its_c_per_step": float(np.mean([s["krylov_its_c"] for s in stats])),
                        "ms_assembly_per_step": float(np.mean([s["ms_assembly"] for s in stats])),
                        "ms_krylov_per_step": float(np.mean([s["ms_krylov"] for s in stats])),
+                       "krylov_its_u_by_step": [int(s["krylov_its_u"]) for s in stats],
                        "final_fnorm": stats[-1]["fnorm"], "parallelism": "vertex partition x%d" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu,

@@ -71,7 +71,8 @@ void apply_pc(glims_ctx* c, int which, int pc, const double* r, double* z, int s
 }
 
 // PCG on block `which` (1: K_uu, 2: K_cc), zero initial guess. Returns iterations, or -1 if not converged.
-constexpr int REC_M = 8;     // directions kept for the successive-RHS projection
+constexpr int REC_KEEP = 8;
+constexpr int REC_M = 30;    // directions kept for the successive-RHS projection (k_multi_dot handles <= 32)
 
 int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_rel, double scale, double tol_abs,
         int maxit, double* res_out, bool recycle = false) {
@@ -153,32 +154,61 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
     cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
     if (recycle) {
         if (result >= 0) {
-            // new direction w = correction, A w = r0 - r_final; A-orthonormalise against the kept ones, append
+            // A w = r0 - r_final for the correction w = x (PCG started from zero on r0)
             double* Aw = r0;
             launch_axpy(c, -1.0, r, Aw, n);
-            const int slot = c->rec_head;
-            double *Un = U + (i64)slot * nl, *AUn = AU + (i64)slot * nl;
-            // (the slot being overwritten is excluded from the projection: project against the other kept ones)
-            launch_copy(c, x, Un, n);
-            launch_copy(c, Aw, AUn, n);
-            for (int k = 0; k < c->rec_n; ++k) {
-                if (k == slot) continue;
-                launch_dot(c, AU + (i64)k * nl, Un, n, S_TMP0);
+            if (c->rec_n >= REC_M) {
+                // basis full: keep the REC_KEEP newest directions and collapse the older ones into the single
+                // direction y = sum_{old} (U_k^T b) U_k they contributed to this solve (A-orthogonal to the rest)
+                const int m = c->rec_n, n_old = m - REC_KEEP;
+                double *y = ws(c, "rec_y", nl), *Ay = ws(c, "rec_Ay", nl);
+                launch_zero(c, y, n);
+                launch_zero(c, Ay, n);
+                launch_multi_axpy(c, U, nl, n_old, coef, 1.0, y, n);       // coef still holds U^T b
+                launch_multi_axpy(c, AU, nl, n_old, coef, 1.0, Ay, n);
+                for (int i = 0; i < REC_KEEP; ++i) {
+                    launch_copy(c, U + (i64)(n_old + i) * nl, U + (i64)(1 + i) * nl, n);
+                    launch_copy(c, AU + (i64)(n_old + i) * nl, AU + (i64)(1 + i) * nl, n);
+                }
+                launch_dot(c, y, Ay, n, S_TMP0);
                 allreduce_scalars(c, S_TMP0, 1);
-                double beta; read_scalars(c, S_TMP0, 1, &beta);
-                launch_axpy(c, -beta, U + (i64)k * nl, Un, n);
-                launch_axpy(c, -beta, AU + (i64)k * nl, AUn, n);
+                double nn; read_scalars(c, S_TMP0, 1, &nn);
+                if (nn > 0 && nn == nn) {
+                    launch_copy(c, y, U, n);
+                    launch_copy(c, Ay, AU, n);
+                    launch_scale(c, 1.0 / std::sqrt(nn), U, n);
+                    launch_scale(c, 1.0 / std::sqrt(nn), AU, n);
+                    c->rec_n = REC_KEEP + 1;
+                } else {
+                    for (int i = 0; i < REC_KEEP; ++i) {
+                        launch_copy(c, U + (i64)(1 + i) * nl, U + (i64)i * nl, n);
+                        launch_copy(c, AU + (i64)(1 + i) * nl, AU + (i64)i * nl, n);
+                    }
+                    c->rec_n = REC_KEEP;
+                }
             }
-            launch_dot(c, Un, AUn, n, S_TMP0);
-            allreduce_scalars(c, S_TMP0, 1);
-            double nn; read_scalars(c, S_TMP0, 1, &nn);
-            if (nn > 0 && nn == nn) {
-                launch_scale(c, 1.0 / std::sqrt(nn), Un, n);
-                launch_scale(c, 1.0 / std::sqrt(nn), AUn, n);
-                if (c->rec_n < REC_M) c->rec_n++;
-                c->rec_head = (slot + 1) % REC_M;
-            } else if (slot < c->rec_n) {     // degenerate direction: drop the slot we clobbered
-                c->rec_n = 0; c->rec_head = 0;
+            {
+                // append w, A-orthonormalised against the kept directions (it already is in exact arithmetic)
+                const int slot = c->rec_n;
+                double *Un = U + (i64)slot * nl, *AUn = AU + (i64)slot * nl;
+                launch_copy(c, x, Un, n);
+                launch_copy(c, Aw, AUn, n);
+                if (slot > 0) {
+                    launch_multi_dot(c, AU, nl, slot, Un, n, S_GM0);
+                    allreduce_scalars(c, S_GM0, slot);
+                    double* coef2 = ws(c, "rec_coef2", 64);
+                    GL_CUDA(cudaMemcpyAsync(coef2, c->scal + S_GM0, sizeof(double) * slot, cudaMemcpyDeviceToDevice, c->stream));
+                    launch_multi_axpy(c, U, nl, slot, coef2, -1.0, Un, n);
+                    launch_multi_axpy(c, AU, nl, slot, coef2, -1.0, AUn, n);
+                }
+                launch_dot(c, Un, AUn, n, S_TMP0);
+                allreduce_scalars(c, S_TMP0, 1);
+                double nn; read_scalars(c, S_TMP0, 1, &nn);
+                if (nn > 0 && nn == nn) {
+                    launch_scale(c, 1.0 / std::sqrt(nn), Un, n);
+                    launch_scale(c, 1.0 / std::sqrt(nn), AUn, n);
+                    c->rec_n = slot + 1;
+                }
             }
         }
         launch_axpy(c, 1.0, xbar, x, n);      // x = x_bar + correction
