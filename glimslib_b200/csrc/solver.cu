@@ -12,6 +12,8 @@ namespace {
 
 struct Pool { std::map<std::string, std::pair<double*, i64>> m; };
 std::map<glims_ctx*, Pool> g_pools;
+struct RecHist { std::vector<std::vector<double>> a; };   // a[j][k]: coefficient of U_k in the j-th most recent solution
+std::map<glims_ctx*, RecHist> g_rec;
 
 double* ws(glims_ctx* c, const char* name, i64 n) {
     auto& e = g_pools[c].m[name];
@@ -26,6 +28,7 @@ double* ws(glims_ctx* c, const char* name, i64 n) {
 void free_pool(glims_ctx* c) {
     for (auto& kv : g_pools[c].m) cudaFree(kv.second.first);
     g_pools.erase(c);
+    g_rec.erase(c);
 }
 
 struct EvTimer {           // accumulates device time of bracketed segments on the stream
@@ -71,7 +74,8 @@ void apply_pc(glims_ctx* c, int which, int pc, const double* r, double* z, int s
 }
 
 // PCG on block `which` (1: K_uu, 2: K_cc), zero initial guess. Returns iterations, or -1 if not converged.
-constexpr int REC_KEEP = 8;
+constexpr int REC_KEEP = 10;   // solutions whose span survives a compression
+
 constexpr int REC_M = 30;    // directions kept for the successive-RHS projection (k_multi_dot handles <= 32)
 
 int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_rel, double scale, double tol_abs,
@@ -99,6 +103,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
             launch_multi_axpy(c, U, nl, c->rec_n, coef, 1.0, x, n);
             launch_multi_axpy(c, AU, nl, c->rec_n, coef, -1.0, r, n);
         }
+        if (c->rec_n == 0) g_rec[c].a.clear();
         launch_copy(c, r, r0, n);
     }
     launch_dot(c, b, b, n, S_BN);
@@ -157,35 +162,55 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
             // A w = r0 - r_final for the correction w = x (PCG started from zero on r0)
             double* Aw = r0;
             launch_axpy(c, -1.0, r, Aw, n);
+            // coefficients of this solve's projection part in the current basis (host copy for the bookkeeping)
+            std::vector<double> acur(REC_M + 1, 0.0);
+            if (c->rec_n > 0) {
+                GL_CUDA(cudaMemcpyAsync(c->h_scal + S_GM0, coef, sizeof(double) * c->rec_n, cudaMemcpyDeviceToHost, c->stream));
+                GL_CUDA(cudaStreamSynchronize(c->stream));
+                for (int k = 0; k < c->rec_n; ++k) acur[k] = c->h_scal[S_GM0 + k];
+            }
+            RecHist& H = g_rec[c];
             if (c->rec_n >= REC_M) {
-                // basis full: keep the REC_KEEP newest directions and collapse the older ones into the single
-                // direction y = sum_{old} (U_k^T b) U_k they contributed to this solve (A-orthogonal to the rest)
-                const int m = c->rec_n, n_old = m - REC_KEEP;
-                double *y = ws(c, "rec_y", nl), *Ay = ws(c, "rec_Ay", nl);
-                launch_zero(c, y, n);
-                launch_zero(c, Ay, n);
-                launch_multi_axpy(c, U, nl, n_old, coef, 1.0, y, n);       // coef still holds U^T b
-                launch_multi_axpy(c, AU, nl, n_old, coef, 1.0, Ay, n);
-                for (int i = 0; i < REC_KEEP; ++i) {
-                    launch_copy(c, U + (i64)(n_old + i) * nl, U + (i64)(1 + i) * nl, n);
-                    launch_copy(c, AU + (i64)(n_old + i) * nl, AU + (i64)(1 + i) * nl, n);
+                // Basis full: compress it to an A-orthonormal basis of span{last REC_KEEP-1 solutions, the
+                // projection part of this one}.  U is A-orthonormal, so Gram-Schmidt on the small coefficient
+                // vectors is Gram-Schmidt in the A-inner product; the new vectors are U * q_i.
+                const int m = c->rec_n;
+                std::vector<std::vector<double>> cand;
+                cand.push_back(std::vector<double>(acur.begin(), acur.begin() + m));
+                for (size_t j = 0; j < H.a.size() && (int)cand.size() < REC_KEEP; ++j)
+                    cand.push_back(std::vector<double>(H.a[j].begin(), H.a[j].begin() + m));
+                std::vector<std::vector<double>> Q;
+                for (auto v : cand) {
+                    double n0 = 0; for (double t : v) n0 += t * t;
+                    for (int pass = 0; pass < 2; ++pass)
+                        for (auto& q : Q) { double d = 0; for (int k = 0; k < m; ++k) d += q[k] * v[k]; for (int k = 0; k < m; ++k) v[k] -= d * q[k]; }
+                    double n1 = 0; for (double t : v) n1 += t * t;
+                    if (n1 > 1e-20 * n0 && n1 > 0) { double inv = 1.0 / std::sqrt(n1); for (auto& t : v) t *= inv; Q.push_back(v); }
                 }
-                launch_dot(c, y, Ay, n, S_TMP0);
-                allreduce_scalars(c, S_TMP0, 1);
-                double nn; read_scalars(c, S_TMP0, 1, &nn);
-                if (nn > 0 && nn == nn) {
-                    launch_copy(c, y, U, n);
-                    launch_copy(c, Ay, AU, n);
-                    launch_scale(c, 1.0 / std::sqrt(nn), U, n);
-                    launch_scale(c, 1.0 / std::sqrt(nn), AU, n);
-                    c->rec_n = REC_KEEP + 1;
-                } else {
-                    for (int i = 0; i < REC_KEEP; ++i) {
-                        launch_copy(c, U + (i64)(1 + i) * nl, U + (i64)i * nl, n);
-                        launch_copy(c, AU + (i64)(1 + i) * nl, AU + (i64)i * nl, n);
-                    }
-                    c->rec_n = REC_KEEP;
+                const int kq = (int)Q.size();
+                double *T = ws(c, "rec_T", nl * REC_KEEP), *AT = ws(c, "rec_AT", nl * REC_KEEP), *qd = ws(c, "rec_q", 64);
+                for (int i = 0; i < kq; ++i) {
+                    GL_CUDA(cudaMemcpyAsync(qd, Q[i].data(), sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+                    launch_zero(c, T + (i64)i * nl, n);
+                    launch_zero(c, AT + (i64)i * nl, n);
+                    launch_multi_axpy(c, U, nl, m, qd, 1.0, T + (i64)i * nl, n);
+                    launch_multi_axpy(c, AU, nl, m, qd, 1.0, AT + (i64)i * nl, n);
+                    GL_CUDA(cudaStreamSynchronize(c->stream));      // qd is reused
                 }
+                for (int i = 0; i < kq; ++i) {
+                    launch_copy(c, T + (i64)i * nl, U + (i64)i * nl, n);
+                    launch_copy(c, AT + (i64)i * nl, AU + (i64)i * nl, n);
+                }
+                // re-express the history and the current projection in the new basis: a' = Q^T a
+                auto reproject = [&](const std::vector<double>& v) {
+                    std::vector<double> o(REC_M + 1, 0.0);
+                    for (int i = 0; i < kq; ++i) { double d = 0; for (int k = 0; k < m; ++k) d += Q[i][k] * v[k]; o[i] = d; }
+                    return o;
+                };
+                for (auto& h : H.a) h = reproject(h);
+                if ((int)H.a.size() > REC_KEEP) H.a.resize(REC_KEEP);
+                acur = reproject(acur);
+                c->rec_n = kq;
             }
             {
                 // append w, A-orthonormalised against the kept directions (it already is in exact arithmetic)
@@ -208,7 +233,10 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
                     launch_scale(c, 1.0 / std::sqrt(nn), Un, n);
                     launch_scale(c, 1.0 / std::sqrt(nn), AUn, n);
                     c->rec_n = slot + 1;
+                    acur[slot] = std::sqrt(nn);
                 }
+                H.a.insert(H.a.begin(), acur);            // newest first
+                if ((int)H.a.size() > REC_KEEP) H.a.resize(REC_KEEP);
             }
         }
         launch_axpy(c, 1.0, xbar, x, n);      // x = x_bar + correction
