@@ -120,6 +120,8 @@ struct glims_ctx {
     double* partials = nullptr;     // block partial sums
     unsigned* tickets = nullptr;
     double* h_scal = nullptr;       // pinned host mirror
+    double* h_ring = nullptr;       // pinned mirror of the PCG r.r ring
+    bool use_graphs = true;         // replay PCG iterations as CUDA graphs (GLIMS_NO_GRAPH=1 disables)
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
 

@@ -813,6 +813,13 @@ __global__ void k_export(const i64* __restrict__ rowptr, const i64* __restrict__
         for (int k = 0; k < NC; ++k) out[t * NC + k] = A[vidx(s, k, NC)];
     }
 }
+// end of a PCG iteration: r.z <- new r.z, append r.r to the ring, bump the iteration counter
+__global__ void k_pcg_shift(double* scal, double* ring) {
+    const int it = (int)ring[64];
+    ring[it & 63] = scal[S_RR];
+    ring[64] = (double)(it + 1);
+    scal[S_RZ] = scal[S_RZNEW];
+}
 __global__ void k_flush(double* buf, i64 n) {
     for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) buf[i] = (double)i;
 }
@@ -1048,6 +1055,10 @@ void read_scalars(glims_ctx* c, int slot0, int n, double* out) {
     GL_CUDA(cudaMemcpyAsync(c->h_scal + slot0, c->scal + slot0, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     GL_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; ++i) out[i] = c->h_scal[slot0 + i];
+}
+void launch_pcg_shift(glims_ctx* c, double* ring) {
+    k_pcg_shift<<<1, 1, 0, c->stream>>>(c->scal, ring);
+    LAUNCHED(c);
 }
 void flush_l2(glims_ctx* c) {
     if (!c->flush_buf) {

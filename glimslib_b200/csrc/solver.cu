@@ -5,13 +5,28 @@
 #include <cstring>
 #include <algorithm>
 #include <map>
+#include <tuple>
+#include <cstdlib>
 
 void launch_split_norms(glims_ctx* c, const double* F, int s0);
+void launch_pcg_shift(glims_ctx* c, double* ring);
 
 namespace {
 
 struct Pool { std::map<std::string, std::pair<double*, i64>> m; };
 std::map<glims_ctx*, Pool> g_pools;
+struct GraphKey {
+    int which, pc; void* amg; void* x; void* r; int bs;
+    bool operator<(const GraphKey& o) const {
+        return std::tie(which, pc, amg, x, r, bs) < std::tie(o.which, o.pc, o.amg, o.x, o.r, o.bs);
+    }
+};
+struct PcgGraph { cudaGraphExec_t exec = nullptr; i64 launches = 0; bool failed = false; };
+std::map<glims_ctx*, std::map<GraphKey, PcgGraph>> g_graphs;
+void free_graphs(glims_ctx* c) {
+    for (auto& kv : g_graphs[c]) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    g_graphs.erase(c);
+}
 struct RecHist { std::vector<std::vector<double>> a; };   // a[j][k]: coefficient of U_k in the j-th most recent solution
 std::map<glims_ctx*, RecHist> g_rec;
 
@@ -29,6 +44,7 @@ void free_pool(glims_ctx* c) {
     for (auto& kv : g_pools[c].m) cudaFree(kv.second.first);
     g_pools.erase(c);
     g_rec.erase(c);
+    free_graphs(c);
 }
 
 struct EvTimer {           // accumulates device time of bracketed segments on the stream
@@ -124,33 +140,59 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
         launch_copy(c, x, xbar, n);
         launch_zero(c, x, n);
     }
-    int cur = S_RZ, nxt = S_RZNEW;
-    apply_pc(c, which, pc, r, z, cur);
-    allreduce_scalars(c, cur, 1);
+    // Every iteration is the same launch sequence (r.z lives in S_RZ, the new one in S_RZNEW and is shifted down
+    // by k_pcg_shift at the end, which also appends r.r to a device ring), so one iteration is captured once into
+    // a CUDA graph and replayed: ~50 launches + NCCL calls per iteration collapse to one cudaGraphLaunch.
+    apply_pc(c, which, pc, r, z, S_RZ);
+    allreduce_scalars(c, S_RZ, 1);
     launch_copy(c, z, p, n);
+    double* ring = ws(c, "pcg_ring", 72);            // [64] r.r history, [64] iteration counter
+    GL_CUDA(cudaMemsetAsync(ring, 0, sizeof(double) * 72, c->stream));
+    if (!c->h_ring) GL_CUDA(cudaMallocHost(&c->h_ring, sizeof(double) * 72));
+    auto iteration = [&]() {
+        halo_exchange(c, p, bs);
+        SpmvDot d; d.w = p; d.slot = S_PAP;
+        launch_spmv(c, which, p, Ap, d);
+        allreduce_scalars(c, S_PAP, 1);
+        launch_cg_update_xr(c, x, r, p, Ap, n, S_RZ, S_PAP, S_RR);
+        apply_pc(c, which, pc, r, z, S_RZNEW);
+        allreduce_scalars(c, S_RR, 2);               // S_RR and S_RZNEW are adjacent: one message
+        launch_cg_update_p(c, p, z, n, S_RZNEW, S_RZ);
+        launch_pcg_shift(c, ring);
+        GL_CUDA(cudaMemcpyAsync(c->h_ring, ring, sizeof(double) * 64, cudaMemcpyDeviceToHost, c->stream));
+    };
+    GraphKey key{which, pc, (void*)c->amg, (void*)x, (void*)r, bs};
+    PcgGraph* G = c->use_graphs ? &g_graphs[c][key] : nullptr;
     cudaEvent_t ev[2];
     cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
-    double* h_rr = c->h_scal + S_COUNT;   // two pinned slots after the mirror
     int result = -1;
     for (int it = 1; it <= maxit + 1; ++it) {
         if (it <= maxit) {
-            halo_exchange(c, p, bs);
-            SpmvDot d; d.w = p; d.slot = S_PAP;
-            launch_spmv(c, which, p, Ap, d);
-            allreduce_scalars(c, S_PAP, 1);
-            launch_cg_update_xr(c, x, r, p, Ap, n, cur, S_PAP, S_RR);
-            apply_pc(c, which, pc, r, z, nxt);
-            allreduce_scalars(c, S_RR, 1);
-            allreduce_scalars(c, nxt, 1);
-            GL_CUDA(cudaMemcpyAsync(&h_rr[it & 1], c->scal + S_RR, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            if (G && G->exec) {
+                GL_CUDA(cudaGraphLaunch(G->exec, c->stream));
+                c->launches += G->launches;
+            } else if (G && !G->failed && it >= 2) {
+                // second iteration of the first solve with this configuration: all buffers exist -> capture
+                i64 l0 = c->launches;
+                cudaGraph_t graph = nullptr;
+                bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+                if (ok) {
+                    try { iteration(); } catch (const GlError&) { ok = false; }
+                    if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess || !graph) ok = false;
+                }
+                if (ok && cudaGraphInstantiate(&G->exec, graph, 0) != cudaSuccess) { ok = false; G->exec = nullptr; }
+                if (graph) cudaGraphDestroy(graph);
+                G->launches = c->launches - l0;
+                c->launches = l0;
+                if (!ok) { G->failed = true; cudaGetLastError(); iteration(); }
+                else { GL_CUDA(cudaGraphLaunch(G->exec, c->stream)); c->launches += G->launches; }
+            } else iteration();
             GL_CUDA(cudaEventRecord(ev[it & 1], c->stream));
-            launch_cg_update_p(c, p, z, n, nxt, cur);
-            std::swap(cur, nxt);
         }
         if (it >= 2) {   // inspect the previous iteration while this one is already queued
             GL_CUDA(cudaEventSynchronize(ev[(it - 1) & 1]));
-            double rn = std::sqrt(h_rr[(it - 1) & 1]);
+            double rn = std::sqrt(c->h_ring[(it - 2) & 63]);
             if (res_out) *res_out = rn;
             if (!(rn == rn)) { result = -1; break; }
             if (rn <= tol) { result = std::min(it, maxit); break; }
@@ -341,6 +383,7 @@ void ensure_kconst(glims_ctx* c, const glims_solver_opts* o) {
         launch_diag_inverse(c, 1);
         c->kconst_valid = true;
         c->rec_n = c->rec_head = 0;
+        free_graphs(c);
         if (c->amg) amg_free(c);
     }
     if (need_amg && !c->amg) amg_setup(c);
@@ -467,6 +510,7 @@ int glims_create(glims_ctx** out, int32_t dim, int64_t n_vertices, const double*
     glims_ctx* c = new glims_ctx();
     *out = c;
     c->device = device;
+    c->use_graphs = std::getenv("GLIMS_NO_GRAPH") == nullptr;
     API_BEGIN
     c->dim = dim; c->nb = dim + 1; c->n_v = n_vertices; c->n_c = n_cells; c->ndof = n_vertices * c->nb;
     if (n_owned >= 0 && n_owned < n_vertices) { c->halo.active = true; c->halo.n_owned = n_owned; }
@@ -517,6 +561,7 @@ int glims_destroy(glims_ctx* c) {
                     (void*)c->tickets, (void*)c->flush_buf, (void*)c->sl_ptr, (void*)c->sl_elem, (void*)c->lent, (void*)c->halo.send_idx, (void*)c->halo.send_buf})
         if (q) cudaFree(q);
     if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->h_ring) cudaFreeHost(c->h_ring);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return GLIMS_OK;
@@ -621,6 +666,8 @@ int glims_assemble(glims_ctx* c, int32_t what, int32_t kernel, int32_t apply_bc)
     if (what & GLIMS_ASM_KCONST) {
         c->kconst_valid = (apply_bc == 2);
         if (c->kconst_valid) launch_diag_inverse(c, 1);
+        free_graphs(c);
+        c->rec_n = 0;
         if (c->amg) amg_free(c);
     }
     GL_CUDA(cudaStreamSynchronize(c->stream));
