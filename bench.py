@@ -159,7 +159,7 @@ def algorithmic_bytes(d, n_v, n_c, nnzb):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=148, help="voxel grid of the C4 ellipsoid (148 -> 10.19M tets)")
