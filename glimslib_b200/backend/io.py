@@ -1,67 +1,87 @@
 """Result writers of the seam: ``File`` (VTK .pvd/.vtu), ``XDMFFile`` and ``HDF5File``.
 
-KNOWN GAP ("next"): no HDF5 library exists in this environment (no h5py / libhdf5), so
-``HDF5File`` and the heavy data of ``XDMFFile`` are stored in a small self-describing binary container with the
-*logical* layout DOLFIN uses (``/<name>/vector_<k>`` datasets, ``count`` / ``timestamp`` attributes,
-helper_classes.py:1256-1308) -- readable by this package, not yet by libhdf5.  The API and the round trip
-(``run`` -> ``solution_timeseries.h5`` -> ``reload_from_hdf5``) work; a byte-level HDF5 writer is the N1 task.
+No HDF5 library exists in this environment (no h5py / libhdf5), so the ``.h5`` files are produced and parsed by
+:mod:`glimslib_b200.backend.minih5`, a from-scratch writer/reader of genuine HDF5 (version-0 superblock, old-style
+groups, contiguous datasets, v1 attributes).  The layout follows DOLFIN's conventions: ``HDF5File.write(f, name, t)``
+appends ``/<name>/vector_<k>`` with a ``timestamp`` attribute and keeps ``count`` on ``/<name>``
+(helper_classes.py:1256-1308); the first write also stores ``cells``, ``cell_dofs`` and ``x_cell_dofs``;
+``XDMFFile`` keeps light data in XML and heavy data in ``<name>.h5`` (helper_classes.py:1360-1375,1436-1437).
 """
-import json
 import os
-import struct
 
 import numpy as np
 
-from . import core
-
-_MAGIC = b"GLIMSB200-H5LIKE-1\n"
+from . import core, minih5
 
 
 class _Container:
-    """Flat {path: ndarray} + {path: {attr: value}} store, written on close."""
+    """Path-addressed view of a minih5 tree: ``data[path]`` datasets, ``attrs[path][name]`` attributes."""
 
     def __init__(self, path, mode):
         self.path, self.mode = path, mode
-        self.data, self.attrs = {}, {}
         if mode in ("r", "a") and os.path.exists(path):
-            self._load()
+            self.root = minih5.read_file(path)
         elif mode == "r":
             raise IOError("cannot open %s" % path)
-
-    def _load(self):
-        with open(self.path, "rb") as f:
-            if f.read(len(_MAGIC)) != _MAGIC:
-                raise IOError("%s is not a glimslib_b200 container (real HDF5 files need the N1 reader)" % self.path)
-            (n,) = struct.unpack("<Q", f.read(8))
-            meta = json.loads(f.read(n).decode())
-            base = f.tell()
-            for name, (dtype, shape, off, size) in meta["data"].items():
-                f.seek(base + off)
-                self.data[name] = np.frombuffer(f.read(size), dtype=dtype).reshape(shape).copy()
-            self.attrs = meta["attrs"]
+        else:
+            self.root = minih5.Group()
+        self.data, self.attrs = _DataView(self.root), _AttrView(self.root)
 
     def flush(self):
         if self.mode == "r":
             return
-        meta, blobs, off = {"data": {}, "attrs": self.attrs}, [], 0
-        for name, a in self.data.items():
-            b = np.ascontiguousarray(a).tobytes()
-            meta["data"][name] = (a.dtype.str, list(a.shape), off, len(b))
-            blobs.append(b)
-            off += len(b)
-        head = json.dumps(meta).encode()
         os.makedirs(os.path.dirname(os.path.abspath(self.path)), exist_ok=True)
-        with open(self.path, "wb") as f:
-            f.write(_MAGIC)
-            f.write(struct.pack("<Q", len(head)))
-            f.write(head)
-            for b in blobs:
-                f.write(b)
+        minih5.write_file(self.path, self.root)
+
+
+class _DataView:
+    def __init__(self, root): self._r = root
+
+    def __setitem__(self, path, arr):
+        self._r.create_dataset(path, np.asarray(arr))
+
+    def __getitem__(self, path):
+        d = self._r.get(path)
+        if not isinstance(d, minih5.Dataset):
+            raise KeyError(path)
+        return d.data
+
+    def __contains__(self, path):
+        return isinstance(self._r.get(path), minih5.Dataset)
+
+
+class _AttrView:
+    """``attrs.setdefault(path, {})[k] = v`` / ``attrs[path][k]`` / ``attrs.get(path, {})`` on groups and datasets."""
+
+    def __init__(self, root): self._r = root
+
+    def _node(self, path, create=False):
+        n = self._r.get(path)
+        if n is None and create:
+            n = self._r.require_group(path)
+        return n
+
+    def setdefault(self, path, default=None):
+        return self._node(path, create=True).attrs
+
+    def __getitem__(self, path):
+        n = self._node(path)
+        if n is None:
+            raise KeyError(path)
+        return n.attrs
+
+    def get(self, path, default=None):
+        n = self._node(path)
+        return default if n is None else n.attrs
 
 
 class _Attributes:
     def __init__(self, store, path): self._s, self._p = store, path.strip("/")
-    def __getitem__(self, k): return self._s.attrs[self._p][k]
+
+    def __getitem__(self, k):
+        v = self._s.attrs[self._p][k]
+        return int(v) if isinstance(v, (np.integer,)) else v
+
     def __setitem__(self, k, v): self._s.attrs.setdefault(self._p, {})[k] = v
     def __contains__(self, k): return k in self._s.attrs.get(self._p, {})
     def to_dict(self): return dict(self._s.attrs.get(self._p, {}))
@@ -79,21 +99,37 @@ class HDF5File:
         c = self._c
         if isinstance(obj, core.Function):
             if timestamp is None:
+                self._write_function_layout(obj, name)
                 c.data[name + "/vector_0"] = obj._x.copy()
-                c.attrs.setdefault(name, {})["count"] = 1
+                c.attrs.setdefault(name, {})["count"] = np.uint64(1)
             else:
-                k = c.attrs.setdefault(name, {}).get("count", 0)
+                k = int(c.attrs.setdefault(name, {}).get("count", 0))
+                if k == 0:
+                    self._write_function_layout(obj, name)
                 c.data["%s/vector_%d" % (name, k)] = obj._x.copy()
                 c.attrs.setdefault("%s/vector_%d" % (name, k), {})["timestamp"] = float(timestamp)
-                c.attrs[name]["count"] = k + 1
+                c.attrs[name]["count"] = np.uint64(k + 1)
         elif isinstance(obj, core.MeshFunction):
             c.data[name + "/values"] = np.asarray(obj.array()).copy()
-            c.attrs.setdefault(name, {})["dim"] = int(obj.dim())
+            c.attrs.setdefault(name, {})["dim"] = np.int64(obj.dim())
         elif hasattr(obj, "coords") and hasattr(obj, "cells"):
             c.data[name + "/coordinates"] = obj.coords.copy()
             c.data[name + "/topology"] = obj.cells.copy()
         else:
             raise TypeError("HDF5File.write: unsupported object %r" % type(obj))
+
+    def _write_function_layout(self, f, name):
+        """``cells`` / ``cell_dofs`` / ``x_cell_dofs`` next to the vectors, as DOLFIN's HDF5File::write(Function) does."""
+        V = f.function_space()
+        m = V.mesh()
+        if V._element.family != "CG":
+            return
+        nc, nvc = m.cells.shape
+        dofs = (m.cells[:, :, None].astype(np.int64) * V.ncomp + np.arange(V.ncomp)[None, None, :]).reshape(nc, -1)
+        c = self._c
+        c.data[name + "/cells"] = np.arange(nc, dtype=np.uint64)
+        c.data[name + "/cell_dofs"] = dofs.ravel()
+        c.data[name + "/x_cell_dofs"] = (np.arange(nc + 1, dtype=np.int64) * dofs.shape[1])
 
     def read(self, obj, name, use_partition_from_file=False):
         name = name.strip("/")
@@ -110,13 +146,13 @@ class HDF5File:
             raise TypeError("HDF5File.read: unsupported object %r" % type(obj))
 
     def attributes(self, name): return _Attributes(self._c, name)
-    def has_dataset(self, name): return name.strip("/") in self._c.data or name.strip("/") in self._c.attrs
+    def has_dataset(self, name): return self._c.root.get(name.strip("/")) is not None
     def flush(self): self._c.flush()
     def close(self): self._c.flush()
 
 
 class XDMFFile:
-    """``solution.xdmf`` (XML light data) + ``solution.h5`` heavy data (see module docstring for the gap).
+    """``solution.xdmf`` (XML light data) + ``solution.h5`` heavy data (HDF5 via minih5).
     ``write(mesh)`` and ``write_checkpoint(function, name, t)`` as used at helper_classes.py:1360-1375,1436-1437."""
 
     class Encoding:
