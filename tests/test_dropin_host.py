@@ -207,3 +207,22 @@ def test_no_gpu_fails_loudly_not_silently(tmp_path, have_gpu):
     from glimslib_b200.engine import EngineError
     with pytest.raises(EngineError):
         sim.run(save_method=None, plot=False, output_dir=str(tmp_path))
+
+
+def test_mesh_hdf5_round_trip(tmp_path):
+    """data_io.save_mesh_hdf5 / read_mesh_hdf5 (reference data_io.py:663-713): mesh + cell and facet labels."""
+    from glimslib_b200.utils import data_io as dio
+    mesh, labels = _labelled_mesh(4, 3)
+    sd = SubDomains(mesh)
+    sd.setup_subdomains(label_function=labels)
+    sd.setup_boundaries(tissue_map={0: "outside", 1: "a", 2: "b"}, boundary_fct_dict={"all": Boundary()})
+    p = str(tmp_path / "mesh.h5")
+    dio.save_mesh_hdf5(mesh, p, subdomains=sd.subdomains, boundaries=sd.named_boundaries)
+    m2, s2, b2 = dio.read_mesh_hdf5(p)
+    assert np.array_equal(m2.cells, mesh.cells) and np.allclose(m2.coords, mesh.coords)
+    assert np.array_equal(s2.array(), sd.subdomains.array()) and np.array_equal(b2.array(), sd.named_boundaries.array())
+    V = fenics.FunctionSpace(m2, "CG", 1)
+    f = fenics.project(fenics.Expression("x[0]+2*x[1]", degree=1), V)
+    dio.save_functions_hdf5({"f": f}, str(tmp_path / "f.h5"), time_step=0)
+    g = dio.read_function_hdf5("f", V, str(tmp_path / "f.h5"))
+    assert np.array_equal(g.vector().get_local(), f.vector().get_local())
