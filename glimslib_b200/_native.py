@@ -32,7 +32,7 @@ class SolverOpts(C.Structure):
     _fields_ = [("snes_rtol", C.c_double), ("snes_atol", C.c_double), ("snes_stol", C.c_double),
                 ("max_newton", C.c_int32), ("ksp_rtol", C.c_double), ("ksp_atol", C.c_double),
                 ("max_krylov", C.c_int32), ("solver", C.c_int32), ("pc", C.c_int32),
-                ("asm_kernel", C.c_int32), ("lag_mechanics", C.c_int32), ("recycle", C.c_int32)]
+                ("asm_kernel", C.c_int32), ("lag_mechanics", C.c_int32), ("recycle", C.c_int32), ("extrapolate", C.c_int32)]
 
 
 class StepStats(C.Structure):

@@ -813,6 +813,12 @@ __global__ void k_export(const i64* __restrict__ rowptr, const i64* __restrict__
         for (int k = 0; k < NC; ++k) out[t * NC + k] = A[vidx(s, k, NC)];
     }
 }
+template <int D>
+__global__ void k_extrapolate_c(double* __restrict__ x, const double* __restrict__ xold, i64 n_v) {
+    constexpr int NB = D + 1;
+    for (i64 v = blockIdx.x * (i64)TPB + threadIdx.x; v < n_v; v += (i64)gridDim.x * TPB)
+        x[v * NB + D] = 2.0 * x[v * NB + D] - xold[v * NB + D];
+}
 // end of a PCG iteration: r.z <- new r.z, append r.r to the ring, bump the iteration counter
 __global__ void k_pcg_shift(double* scal, double* ring) {
     const int it = (int)ring[64];
@@ -1055,6 +1061,11 @@ void read_scalars(glims_ctx* c, int slot0, int n, double* out) {
     GL_CUDA(cudaMemcpyAsync(c->h_scal + slot0, c->scal + slot0, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     GL_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; ++i) out[i] = c->h_scal[slot0 + i];
+}
+void launch_extrapolate_c(glims_ctx* c, double* x, const double* xold) {
+    if (c->dim == 2) k_extrapolate_c<2><<<red_grid(c, c->n_v), TPB, 0, c->stream>>>(x, xold, c->n_v);
+    else k_extrapolate_c<3><<<red_grid(c, c->n_v), TPB, 0, c->stream>>>(x, xold, c->n_v);
+    LAUNCHED(c);
 }
 void launch_pcg_shift(glims_ctx* c, double* ring) {
     k_pcg_shift<<<1, 1, 0, c->stream>>>(c->scal, ring);

@@ -10,6 +10,7 @@
 
 void launch_split_norms(glims_ctx* c, const double* F, int s0);
 void launch_pcg_shift(glims_ctx* c, double* ring);
+void launch_extrapolate_c(glims_ctx* c, double* x, const double* xold);
 
 namespace {
 
@@ -501,6 +502,7 @@ void glims_default_opts(glims_solver_opts* o) {
     o->solver = GLIMS_SOLVER_BLOCK_TRI; o->pc = GLIMS_PC_AMG; o->asm_kernel = GLIMS_ASMK_ATOMIC;
     o->lag_mechanics = 1;
     o->recycle = 1;
+    o->extrapolate = 0;
 }
 
 int glims_create(glims_ctx** out, int32_t dim, int64_t n_vertices, const double* coords, int64_t n_cells,
@@ -627,9 +629,9 @@ static int copy_vec(glims_ctx* c, double* dev, double* host_out, const double* h
     GL_CUDA(cudaStreamSynchronize(c->stream));
     API_END
 }
-int glims_set_state(glims_ctx* c, const double* x) { return x ? copy_vec(c, c ? c->x : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
+int glims_set_state(glims_ctx* c, const double* x) { if (c) c->have_hist = false; return x ? copy_vec(c, c ? c->x : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
 int glims_get_state(glims_ctx* c, double* x) { return x ? copy_vec(c, c ? c->x : nullptr, x, nullptr) : GLIMS_ERR_ARG; }
-int glims_set_prev(glims_ctx* c, const double* x) { return x ? copy_vec(c, c ? c->xprev : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
+int glims_set_prev(glims_ctx* c, const double* x) { if (c) c->have_hist = false; return x ? copy_vec(c, c ? c->xprev : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
 int glims_get_prev(glims_ctx* c, double* x) { return x ? copy_vec(c, c ? c->xprev : nullptr, x, nullptr) : GLIMS_ERR_ARG; }
 int64_t glims_ndof(const glims_ctx* c) { return c ? c->ndof : 0; }
 int64_t glims_nnzb(const glims_ctx* c) { return c ? c->pat.nnzb : 0; }
@@ -643,11 +645,26 @@ int glims_step(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, glims_
     if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_step before glims_set_materials");
     glims_solver_opts od;
     if (!o) { glims_default_opts(&od); o = &od; }
+    double* backup = ws(c, "step_backup", c->ndof);
     for (int s = 0; s < n_steps; ++s) {
-        newton_step(c, o, stats ? &stats[s] : nullptr);
+        // keep the last good iterate: a failed step leaves the state where the previous step ended
+        launch_copy(c, c->x, backup, c->ndof);
+        if (o->extrapolate && c->have_hist) {
+            // first Newton guess: c_n + (c_n - c_{n-1}); only the start of the iteration changes, not its fixed point
+            launch_extrapolate_c(c, c->x, ws(c, "x_hist", c->ndof));
+        }
+        try {
+            newton_step(c, o, stats ? &stats[s] : nullptr);
+        } catch (const GlError&) {
+            launch_copy(c, backup, c->x, c->ndof);
+            cudaStreamSynchronize(c->stream);
+            throw;
+        }
         // u_previous.assign(solution)  (simulation_base.py:312); ghosts refreshed first so that the next
         // step's residual sees the converged c_prev on the overlap cells
         halo_exchange(c, c->x, c->nb);
+        launch_copy(c, c->xprev, ws(c, "x_hist", c->ndof), c->ndof);     // solution of the step before this one
+        c->have_hist = true;
         launch_copy(c, c->x, c->xprev, c->ndof);
     }
     GL_CUDA(cudaStreamSynchronize(c->stream));

@@ -57,7 +57,7 @@ typedef struct {
        simulation_tumor_growth.py:126-130 leaves untouched */
     double snes_rtol;        /* 1e-9  */
     double snes_atol;        /* 1e-10 */
-    double snes_stol;        /* 1e-16 */
+    double snes_stol;        /* 1e-16; accepted for parity with DOLFIN's parameter set, not used as a stopping test */
     int32_t max_newton;      /* 50    */
     double ksp_rtol;         /* relative to |rhs| of each linear solve */
     double ksp_atol;         /* absolute floor for the linear residual */
@@ -69,6 +69,9 @@ typedef struct {
                                 (same fixed point; the displacement does not feed back, stg:110-120) */
     int32_t recycle;         /* 1: project every K_uu solve onto the A-orthonormalised corrections of the previous
                                 (up to 8) solves before PCG starts -- K_uu is constant, the loads vary smoothly in time */
+    int32_t extrapolate;     /* 1: first Newton guess of a step = c_n + (c_n - c_{n-1}) once two solutions exist
+                                (the reference starts from c_n; default 0: measured at C4 it lowers the final |F| but not the
+                                Newton iteration count) */
 } glims_solver_opts;
 
 typedef struct {

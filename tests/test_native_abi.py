@@ -39,3 +39,34 @@ def test_null_context_is_an_error_not_a_crash():
     lib = N.load()
     assert lib.glims_set_dt(None, 1.0) == N.ERR_ARG
     assert lib.glims_destroy(None) == N.ERR_ARG
+
+
+def test_create_rejects_bad_arguments_before_touching_cuda():
+    """Argument validation happens before any CUDA call, so it is testable without a GPU."""
+    import numpy as np
+    lib = N.load()
+    h = ctypes.c_void_p()
+    xy = np.zeros((3, 2))
+    cells = np.array([[0, 1, 2]], dtype=np.int32)
+    mat = np.zeros(1, dtype=np.int32)
+    args = (N.as_dp(xy), 1, N.as_ip(cells), N.as_ip(mat), -1, 0)
+    assert lib.glims_create(ctypes.byref(h), 4, 3, *args) == N.ERR_ARG          # dim must be 2 or 3
+    assert lib.glims_create(ctypes.byref(h), 2, 0, *args) == N.ERR_ARG          # empty vertex set
+    assert lib.glims_create(ctypes.byref(h), 2, 3, N.as_dp(xy), 0, N.as_ip(cells), N.as_ip(mat), -1, 0) == N.ERR_ARG
+    assert lib.glims_create(ctypes.byref(h), 2, 3, None, 1, N.as_ip(cells), N.as_ip(mat), -1, 0) == N.ERR_ARG
+    assert lib.glims_create(None, 2, 3, *args) == N.ERR_ARG
+
+
+def test_engine_validates_host_arrays_before_the_abi():
+    import numpy as np
+    import pytest
+    from glimslib_b200.engine import Engine
+    xy = np.zeros((3, 2))
+    with pytest.raises(ValueError):
+        Engine(xy, np.array([[0, 1, 3]]), np.zeros(1))                            # vertex index out of range
+    with pytest.raises(ValueError):
+        Engine(xy, np.array([[0, 1, 2, 2]]), np.zeros(1))                         # tets on 2D coordinates
+    with pytest.raises(ValueError):
+        Engine(np.zeros((3, 4)), np.array([[0, 1, 2]]), np.zeros(1))              # 4D coordinates
+    with pytest.raises(ValueError):
+        Engine(xy, np.array([[0, 1, 2]]), np.zeros(2))                            # ragged labels
