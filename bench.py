@@ -271,7 +271,11 @@ def main():
             kernels[name] = {"ms": ms, "algorithmic_bytes": ab[key], "achieved_gbs": gbs, "frac": gbs / peak}
         k = kernels["spmv_kuu"]
         roof = {"bound": "hbm", "kernel": "k_spmv_block<3,3> (K_uu SELL-32 SpMV inside PCG)", "achieved": k["achieved_gbs"],
-                "peak": peak, "unit": "GB/s", "frac": k["frac"], "traffic": None, "peak_source": peak_src}
+                "peak": peak, "unit": "GB/s", "frac": k["frac"],
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
+                # kernel on this workload (profiles/r01_ncu_summary.md); only valid for the default mesh on one GPU
+                "traffic": 2.070e9 if (args.n == 148 and world == 1) else None,
+                "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, r01)", "peak_source": peak_src}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
