@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--n", type=int, default=148, help="voxel grid of the C4 ellipsoid (148 -> 10.19M tets)")
+    ap.add_argument("--grid", dest="n", type=int, default=148, help="voxel grid of the C4 ellipsoid (148 -> 10.19M tets)")
     ap.add_argument("--pc", default="amg", choices=["amg", "amg64", "jacobi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")

@@ -603,3 +603,19 @@ def norm(f, norm_type="L2"):
     v = f.node_values() if isinstance(f, Function) else f.values()
     m = (f if isinstance(f, Function) else f.function).function_space().mesh()
     return float(np.sqrt(max(_mass_apply(m, v.shape[1], v), 0.0)))
+
+
+# ------------------------------------------------------------------------------------------------ UFL algebra
+def _no_ufl(name):
+    def f(*a, **k):
+        raise NotImplementedError(
+            "fenics.%s: UFL form algebra is not part of the B200 backend -- the coupled RD-mechanics weak form "
+            "(simulation_tumor_growth.py:110-124) is evaluated in closed form by the CUDA element kernels and "
+            "described to the solver by CoupledRDMechanicsForm" % name)
+    f.__name__ = name
+    return f
+
+
+inner, grad, sym, tr, det, dot, div, sqrt, derivative, Identity, assemble, solve = (
+    _no_ufl(n) for n in ("inner", "grad", "sym", "tr", "det", "dot", "div", "sqrt", "derivative", "Identity",
+                         "assemble", "solve"))

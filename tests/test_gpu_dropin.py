@@ -72,3 +72,46 @@ def test_rerun_with_new_parameters_reuses_the_engine(tmp_path):
     sim.run(save_method=None, plot=False, output_dir=str(tmp_path))
     assert sim.solver._engine is eng
     assert sim.solution.vector().get_local()[2::3].sum() < c_end.sum()
+
+
+def test_brain_variant_agrees_with_dict_parameters(tmp_path):
+    """The reference's own cross-check (test_case_comparison_2D_atlas.py): TumorGrowth with per-tissue dicts and
+    TumorGrowthBrain with per-tissue scalars give the same fields. Four tissues on a 2D strip mesh, 5 steps."""
+    from glimslib_b200 import fenics_local as fenics
+    from glimslib_b200.simulation.simulation_tumor_growth import TumorGrowth
+    from glimslib_b200.simulation.simulation_tumor_growth_brain import TumorGrowthBrain
+
+    class Boundary(fenics.SubDomain):
+        def inside(self, x, on_boundary):
+            return on_boundary
+
+    mesh = fenics.RectangleMesh(fenics.Point(0, 0), fenics.Point(8, 4), 64, 32)
+    sd = fenics.MeshFunction("size_t", mesh, 2)
+    xm = mesh.cell_midpoints()[:, 0]
+    sd.array()[:] = np.where(xm < 2, 1, np.where(xm < 4, 2, np.where(xm < 6, 3, 4)))
+    tm = {1: "CSF", 2: "GM", 3: "WM", 4: "Ventricles"}
+    bcs = {"clamped": {"bc_value": fenics.Constant((0.0, 0.0)), "named_boundary": "all", "subspace_id": 0}}
+    ivs = {0: fenics.Constant((0.0, 0.0)),
+           1: fenics.Expression("exp(-a*pow(x[0]-x0,2)-a*pow(x[1]-y0,2))", degree=1, a=2.0, x0=4.0, y0=2.0)}
+    a = TumorGrowth(mesh)
+    a.setup_global_parameters(subdomains=sd, domain_names=tm, boundaries={"all": Boundary()}, dirichlet_bcs=bcs)
+    a.setup_model_parameters(iv_expression=ivs, sim_time=5, sim_time_step=1,
+                             E={"CSF": 1e-3, "GM": 3e-3, "WM": 3e-3, "Ventricles": 1e-3},
+                             poisson={"CSF": 0.47, "GM": 0.4, "WM": 0.4, "Ventricles": 0.3},
+                             diffusion={"CSF": 0, "GM": 0.02, "WM": 0.1, "Ventricles": 0},
+                             proliferation={"CSF": 0, "GM": 0.05, "WM": 0.05, "Ventricles": 0},
+                             coupling={"CSF": 0.1, "GM": 0.1, "WM": 0.1, "Ventricles": 0.1})
+    a.run(save_method=None, plot=False, output_dir=str(tmp_path / "a"))
+    b = TumorGrowthBrain(mesh)
+    b.setup_global_parameters(subdomains=sd, domain_names=tm, boundaries={"all": Boundary()}, dirichlet_bcs=bcs)
+    b.setup_model_parameters(iv_expression=ivs, sim_time=5, sim_time_step=1, E_GM=3e-3, E_WM=3e-3, E_CSF=1e-3, E_VENT=1e-3,
+                             nu_GM=0.4, nu_WM=0.4, nu_CSF=0.47, nu_VENT=0.3, D_GM=0.02, D_WM=0.1, rho_GM=0.05,
+                             rho_WM=0.05, coupling=0.1)
+    b.run(save_method=None, plot=False, output_dir=str(tmp_path / "b"))
+    assert a.results.get_recording_steps() == b.results.get_recording_steps() == list(range(6))
+    xa, xb = a.solution.vector().get_local(), b.solution.vector().get_local()
+    assert np.abs(xa).max() > 0
+    assert fenics.errornorm(a.solution, b.solution) <= 1e-9 * fenics.norm(a.solution)
+    # comparison metric of the reference (helper_classes.py:2001-2013) on the concentration sub-function
+    ca, cb = a.solution.sub(1, deepcopy=True), b.solution.sub(1, deepcopy=True)
+    assert fenics.errornorm(ca, cb) <= 1e-9 * fenics.norm(ca)
