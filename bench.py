@@ -21,7 +21,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line (NCCL prints its version otherwise)
 
 METRIC = "timesteps/sec, 3D 10M-tet coupled RD-mechanics (config C4)"
 UNIT = "timesteps/s"
@@ -170,6 +169,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: everything libraries print (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from glimslib_b200 import _native as N
     from glimslib_b200 import workloads as W
@@ -303,7 +305,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
         import torch.distributed as dist
