@@ -17,7 +17,7 @@ SYMBOLS = [
     "glims_set_dt", "glims_set_dirichlet", "glims_set_load", "glims_set_state", "glims_get_state",
     "glims_set_prev", "glims_get_prev", "glims_ndof", "glims_nnzb", "glims_nslots", "glims_state_dev",
     "glims_stream", "glims_step", "glims_assemble", "glims_get_residual", "glims_export_pattern",
-    "glims_export_values", "glims_spmv", "glims_time_kernel", "glims_launch_count",
+    "glims_export_values", "glims_spmv", "glims_time_kernel", "glims_launch_count", "glims_cell_fields",
     "glims_nccl_unique_id", "glims_comm_init", "glims_set_halo",
 ]
 
@@ -85,6 +85,7 @@ def load():
         "glims_spmv": (i32, [p, i32, dp, dp]),
         "glims_time_kernel": (i32, [p, i32, i32, i32, i32, C.POINTER(C.c_float)]),
         "glims_launch_count": (i64, [p]),
+        "glims_cell_fields": (i32, [p, dp, dp]),
         "glims_nccl_unique_id": (i32, [p]),
         "glims_comm_init": (i32, [p, i32, i32, p]),
         "glims_set_halo": (i32, [p, i32, ip, lp, ip, lp]),

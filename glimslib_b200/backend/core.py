@@ -263,6 +263,19 @@ class VectorElement(FiniteElement):
     def num_sub_elements(self): return self.ncomp
 
 
+class TensorElement(FiniteElement):
+    def __init__(self, family, cell=None, degree=1, shape=None):
+        super().__init__(family, cell, degree)
+        d = {"triangle": 2, "tetrahedron": 3, "interval": 1}[cell]
+        self.shape = shape or (d, d)
+        self.ncomp = int(np.prod(self.shape))
+
+    def sub_elements(self):
+        return [FiniteElement(self.family, self.cell, self.degree) for _ in range(self.ncomp)]
+
+    def num_sub_elements(self): return self.ncomp
+
+
 class MixedElement:
     def __init__(self, *elements):
         self._subs = list(elements[0]) if len(elements) == 1 and isinstance(elements[0], (list, tuple)) else list(elements)
@@ -330,6 +343,10 @@ class FunctionSpace:
             return np.arange(self.dim())
         n = self._parent.n_nodes()
         return (np.arange(n)[:, None] * self._parent.ncomp + np.arange(*self._comps)[None, :]).ravel()
+
+
+def TensorFunctionSpace(mesh, family, degree, shape=None):
+    return FunctionSpace(mesh, TensorElement(family, mesh.ufl_cell(), degree, shape))
 
 
 def VectorFunctionSpace(mesh, family, degree, dim=None):

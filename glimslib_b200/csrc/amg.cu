@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <cstdlib>
 
 namespace {
 
@@ -688,6 +689,8 @@ void amg_setup(glims_ctx* c) {
     c->amg = amg;
     const int D = c->dim;
     amg->dim = D;
+    if (const char* e = std::getenv("GLIMS_AMG_DEGREE")) amg->cheb_degree = std::max(1, atoi(e));
+    if (const char* e = std::getenv("GLIMS_AMG_RATIO")) amg->cheb_ratio = atof(e);
     const int bsc = (D == 2) ? 3 : 6;
     GL_CUDA(cudaStreamSynchronize(c->stream));
 

@@ -399,6 +399,109 @@ k_assemble_slice(const double* __restrict__ coords, const int* __restrict__ cell
     }
 }
 
+// N2 derived fields, one thread per cell (P1 displacement => strain and stress are constant per cell):
+// out[e][*] = strain (d*d), stress (d*d), pressure = tr(sigma)/3, von Mises, det(I + grad u),
+// det(I + cbar*gamma*I), logistic growth rho*cbar*(1-cbar)   (math_linear_elasticity.py:12-46, math_reaction_diffusion.py:2-3)
+template <int D>
+__global__ void k_cell_fields(const double* __restrict__ coords, const int* __restrict__ cells,
+                              const int* __restrict__ cell_mat, const double* __restrict__ mat_g, int n_mat, i64 n_c,
+                              const double* __restrict__ x, double* __restrict__ out, double* __restrict__ vol_out) {
+    constexpr int NB = D + 1, NF = 2 * D * D + 5;
+    __shared__ double smat[MAX_MAT * MAT_STRIDE];
+    for (int t = threadIdx.x; t < n_mat * MAT_STRIDE; t += blockDim.x) smat[t] = mat_g[t];
+    __syncthreads();
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= n_c) return;
+    int v[NB];
+    double X[NB][D];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) {
+        v[a] = cells[e * NB + a];
+#pragma unroll
+        for (int k = 0; k < D; ++k) X[a][k] = coords[(i64)v[a] * D + k];
+    }
+    Geo<D> G;
+    geometry(X, G);
+    const double* m = &smat[cell_mat[e] * MAT_STRIDE];
+    const double mu = m[0], lam = m[1], rho = m[3], gam = m[4];
+    double gu[D][D], cbar = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) gu[i][j] = 0;
+#pragma unroll
+    for (int a = 0; a < NB; ++a) {
+        cbar += x[(i64)v[a] * NB + D] * (1.0 / NB);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const double ui = x[(i64)v[a] * NB + i];
+#pragma unroll
+            for (int j = 0; j < D; ++j) gu[i][j] += ui * G.g[a][j];
+        }
+    }
+    double* o = out + e * NF;
+    double tr = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) tr += gu[i][i];
+    double sig[D][D], trs = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double eps = 0.5 * (gu[i][j] + gu[j][i]);
+            o[i * D + j] = eps;
+            sig[i][j] = 2.0 * mu * eps + (i == j ? lam * tr : 0.0);
+            o[D * D + i * D + j] = sig[i][j];
+        }
+#pragma unroll
+    for (int i = 0; i < D; ++i) trs += sig[i][i];
+    o[2 * D * D] = trs * (1.0 / 3.0);                                  // compute_pressure_from_stress_tensor: 1/3 tr
+    double dev2 = 0;                                                   // deviator uses 1/3 tr I_d (mle:35-36) in 2D too
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double dv = sig[i][j] - (i == j ? trs * (1.0 / 3.0) : 0.0);
+            dev2 += dv * dv;
+        }
+    o[2 * D * D + 1] = sqrt(1.5 * dev2);
+    double F[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) F[i][j] = gu[i][j] + (i == j ? 1.0 : 0.0);
+    double detF;
+    if (D == 2) detF = F[0][0] * F[1][1] - F[0][1] * F[1][0];
+    else detF = F[0][0] * (F[1][1] * F[2 % D][2 % D] - F[1][2 % D] * F[2 % D][1]) - F[0][1] * (F[1][0] * F[2 % D][2 % D] - F[1][2 % D] * F[2 % D][0])
+              + F[0][2 % D] * (F[1][0] * F[2 % D][1] - F[1][1] * F[2 % D][0]);
+    o[2 * D * D + 2] = detF;
+    double jg = 1.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) jg *= (1.0 + cbar * gam);
+    o[2 * D * D + 3] = jg;
+    o[2 * D * D + 4] = rho * cbar * (1.0 - cbar);
+    vol_out[e] = G.vol;
+}
+
+// volume-weighted nodal average of per-cell fields: num[v][f] += vol*q, den[v] += vol
+__global__ void k_cell_to_vertex(const int* __restrict__ cells, int nb, i64 n_c, int nf, const double* __restrict__ q,
+                                 const double* __restrict__ vol, double* num, double* den) {
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= n_c) return;
+    const double w = vol[e];
+    for (int a = 0; a < nb; ++a) {
+        const i64 v = cells[e * nb + a];
+        atomicAdd(&den[v], w);
+        for (int f = 0; f < nf; ++f) atomicAdd(&num[v * nf + f], w * q[e * nf + f]);
+    }
+}
+__global__ void k_divide_rows(double* num, const double* __restrict__ den, i64 n_v, int nf) {
+    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (t >= n_v * nf) return;
+    const double d = den[t / nf];
+    num[t] = d > 0 ? num[t] / d : 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3 Dirichlet
 __global__ void k_bc_values(const i64* __restrict__ dofs, const double* __restrict__ vals, i64 n, double* x) {
@@ -1061,6 +1164,19 @@ void read_scalars(glims_ctx* c, int slot0, int n, double* out) {
     GL_CUDA(cudaMemcpyAsync(c->h_scal + slot0, c->scal + slot0, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     GL_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; ++i) out[i] = c->h_scal[slot0 + i];
+}
+void launch_cell_fields(glims_ctx* c, double* out, double* vol) {
+    int g = nblk(c->n_c, 128);
+    if (c->dim == 2) k_cell_fields<2><<<g, 128, 0, c->stream>>>(c->coords, c->cells, c->cell_mat, c->mat, c->n_mat, c->n_c, c->x, out, vol);
+    else k_cell_fields<3><<<g, 128, 0, c->stream>>>(c->coords, c->cells, c->cell_mat, c->mat, c->n_mat, c->n_c, c->x, out, vol);
+    LAUNCHED(c);
+}
+void launch_cell_to_vertex(glims_ctx* c, int nf, const double* q, const double* vol, double* num, double* den) {
+    GL_CUDA(cudaMemsetAsync(num, 0, sizeof(double) * c->n_v * nf, c->stream));
+    GL_CUDA(cudaMemsetAsync(den, 0, sizeof(double) * c->n_v, c->stream));
+    k_cell_to_vertex<<<nblk(c->n_c), TPB, 0, c->stream>>>(c->cells, c->nb, c->n_c, nf, q, vol, num, den);
+    k_divide_rows<<<nblk(c->n_v * nf), TPB, 0, c->stream>>>(num, den, c->n_v, nf);
+    c->launches += 2;
 }
 void launch_extrapolate_c(glims_ctx* c, double* x, const double* xold) {
     if (c->dim == 2) k_extrapolate_c<2><<<red_grid(c, c->n_v), TPB, 0, c->stream>>>(x, xold, c->n_v);

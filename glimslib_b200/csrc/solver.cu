@@ -11,6 +11,8 @@
 void launch_split_norms(glims_ctx* c, const double* F, int s0);
 void launch_pcg_shift(glims_ctx* c, double* ring);
 void launch_extrapolate_c(glims_ctx* c, double* x, const double* xold);
+void launch_cell_fields(glims_ctx* c, double* out, double* vol);
+void launch_cell_to_vertex(glims_ctx* c, int nf, const double* q, const double* vol, double* num, double* den);
 
 namespace {
 
@@ -728,6 +730,22 @@ int glims_spmv(glims_ctx* c, int32_t which, const double* x, double* y) {
     halo_exchange(c, dx, bs);
     launch_spmv(c, which, dx, dy);
     GL_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * c->pat.n_rows * bs, cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_cell_fields(glims_ctx* c, double* cell_out, double* vertex_out) {
+    API_BEGIN
+    if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_cell_fields before glims_set_materials");
+    const int nf = 2 * c->dim * c->dim + 5;
+    double *q = ws(c, "pp_q", c->n_c * nf), *vol = ws(c, "pp_vol", c->n_c);
+    launch_cell_fields(c, q, vol);
+    if (cell_out) GL_CUDA(cudaMemcpyAsync(cell_out, q, sizeof(double) * c->n_c * nf, cudaMemcpyDeviceToHost, c->stream));
+    if (vertex_out) {
+        double *num = ws(c, "pp_num", c->n_v * nf), *den = ws(c, "pp_den", c->n_v);
+        launch_cell_to_vertex(c, nf, q, vol, num, den);
+        GL_CUDA(cudaMemcpyAsync(vertex_out, num, sizeof(double) * c->n_v * nf, cudaMemcpyDeviceToHost, c->stream));
+    }
     GL_CUDA(cudaStreamSynchronize(c->stream));
     API_END
 }

@@ -162,6 +162,22 @@ class Engine:
         self._check(self._lib.glims_spmv(self._h, which, N.as_dp(a), N.as_dp(y)), "spmv")
         return y
 
+    FIELD_NAMES = ("strain", "stress", "pressure", "von_mises", "total_jacobian", "growth_jacobian", "logistic_growth")
+
+    def cell_fields(self, vertex=False):
+        """Derived fields of the current device state. Returns a dict of per-cell arrays (or volume-weighted nodal
+        averages with ``vertex=True``): strain/stress [n, d, d], the rest [n]."""
+        d = self.dim
+        nf = 2 * d * d + 5
+        n = self.n_vertices if vertex else self.n_cells
+        out = np.empty((n, nf))
+        args = (None, N.as_dp(out)) if vertex else (N.as_dp(out), None)
+        self._check(self._lib.glims_cell_fields(self._h, *args), "cell_fields")
+        res = {"strain": out[:, :d * d].reshape(n, d, d), "stress": out[:, d * d:2 * d * d].reshape(n, d, d)}
+        for k, name in enumerate(self.FIELD_NAMES[2:]):
+            res[name] = out[:, 2 * d * d + k]
+        return res
+
     def time_kernel(self, kernel, variant=0, reps=10, flush_l2=True):
         ms = C.c_float()
         self._check(self._lib.glims_time_kernel(self._h, kernel, variant, reps, int(flush_l2), C.byref(ms)), "time_kernel")

@@ -81,4 +81,5 @@ class TumorGrowth(FenicsSimulation):
         return self.solution
 
     def init_postprocess(self, output_dir=config.output_dir_simulation_tmp):
-        self.postprocess = PostProcessTumorGrowth(self.results, self.params, output_dir=output_dir)
+        self.postprocess = PostProcessTumorGrowth(self.results, self.params, output_dir=output_dir,
+                                                  engine=getattr(getattr(self, "solver", None), "_engine", None))

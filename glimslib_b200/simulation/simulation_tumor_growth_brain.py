@@ -63,4 +63,5 @@ class TumorGrowthBrain(TumorGrowth):
         return self.solution
 
     def init_postprocess(self, output_dir=config.output_dir_simulation_tmp):
-        self.postprocess = PostProcessTumorGrowthBrain(self.results, self.params, output_dir=output_dir)
+        self.postprocess = PostProcessTumorGrowthBrain(self.results, self.params, output_dir=output_dir,
+                                                       engine=getattr(getattr(self, "solver", None), "_engine", None))

@@ -760,14 +760,71 @@ class Plotting:
 
 
 class PostProcessTumorGrowth:
-    """Derived-field post-processing is a 'next' row; the handle exists so that
-    ``sim.init_postprocess`` does not fail, but it computes nothing yet."""
+    """Derived fields of recorded solutions (reference: helper_classes.py:1560-1618,1736-1786).
 
-    def __init__(self, results, params, output_dir=None, plot_params=None):
-        self.results, self.params, self.output_dir = results, params, output_dir
+    The reference L2-projects UFL expressions (one CG+AMG solve per field per step).  With P1 displacement, strain,
+    stress, pressure, von Mises and det(I + grad u) are constant per cell, so here one device kernel evaluates them per
+    cell (``glims_cell_fields``) and, for the P1 fields the reference returns, takes the volume-weighted nodal average
+    (the lumped-mass L2 projection).  ``cellwise=True`` returns the exact per-cell (DG0) values instead.
+    Plotting / ALE mesh motion stay out of scope."""
 
-    def __getattr__(self, name):
-        raise NotImplementedError("PostProcess.%s: derived fields are not implemented in the B200 backend yet" % name)
+    def __init__(self, results, params, output_dir=None, plot_params=None, engine=None):
+        self.logger = logging.getLogger(__name__)
+        self._results, self._params, self._output_dir = results, params, output_dir
+        self._functionspace = results._functionspace
+        self._mesh = self._functionspace._mesh
+        self._engine = engine
+
+    def set_output_dir(self, output_dir): self._output_dir = output_dir
+    def get_output_dir(self): return self._output_dir
+
+    def get_solution_displacement(self, recording_step=None):
+        return self._results.get_solution_function(subspace_name="displacement", recording_step=recording_step)
+
+    def get_solution_concentration(self, recording_step=None):
+        return self._results.get_solution_function(subspace_name="concentration", recording_step=recording_step)
+
+    def _fields(self, recording_step, cellwise):
+        if self._engine is None:
+            raise RuntimeError("post-processing needs the simulation's engine: call sim.init_postprocess() after sim.run()")
+        u = self._results.get_solution_function(recording_step=recording_step)
+        self._engine.set_state(u.vector().get_local())
+        return self._engine.cell_fields(vertex=not cellwise)
+
+    def _as_function(self, values, name, cellwise, tensor=False):
+        fam, deg = ("DG", 0) if cellwise else ("Lagrange", 1)
+        V = fenics.TensorFunctionSpace(self._mesh, fam, deg) if tensor else fenics.FunctionSpace(self._mesh, fam, deg)
+        f = fenics.Function(V, name=name)
+        f.vector().set_local(np.asarray(values).reshape(-1))
+        return f
+
+    def get_strain_tensor(self, recording_step=None, cellwise=False):
+        return self._as_function(self._fields(recording_step, cellwise)["strain"], "strain_tensor", cellwise, tensor=True)
+
+    def get_stress_tensor(self, recording_step=None, cellwise=False):
+        return self._as_function(self._fields(recording_step, cellwise)["stress"], "stress_tensor", cellwise, tensor=True)
+
+    def get_pressure(self, recording_step=None, cellwise=False):
+        return self._as_function(self._fields(recording_step, cellwise)["pressure"], "pressure", cellwise)
+
+    def get_van_mises_stress(self, recording_step=None, cellwise=False):
+        return self._as_function(self._fields(recording_step, cellwise)["von_mises"], "van_mises_stress", cellwise)
+
+    def get_total_jacobian(self, recording_step=None, cellwise=False):
+        return self._as_function(self._fields(recording_step, cellwise)["total_jacobian"], "total_jacobian", cellwise)
+
+    def get_growth_induced_jacobian(self, recording_step=None, cellwise=False):
+        return self._as_function(self._fields(recording_step, cellwise)["growth_jacobian"], "growth_induced_jacobian", cellwise)
+
+    def get_logistic_growth(self, recording_step=None, cellwise=False):
+        return self._as_function(self._fields(recording_step, cellwise)["logistic_growth"], "log_growth", cellwise)
+
+    def get_displacement_norm(self, recording_step=None):
+        u = self.get_solution_displacement(recording_step=recording_step)
+        return self._as_function(np.linalg.norm(u.node_values(), axis=1), "displacement_norm", False)
+
+    def plot_all(self, *a, **k):
+        self.logger.warning("plotting is not part of the B200 hot path -- skipping plots")
 
 
 PostProcessTumorGrowthBrain = PostProcessTumorGrowth

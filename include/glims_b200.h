@@ -150,6 +150,12 @@ int glims_spmv(glims_ctx* c, int32_t which, const double* x, double* y);
    >L2-sized buffer between launches (outside the timed events). */
 int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t reps, int32_t flush_l2,
                       float* ms_avg);
+/* Derived fields of the current state (PostProcessTumorGrowth, helper_classes.py:1560-1618,1736-1786), evaluated per
+   cell on the device instead of by L2 projections: for every cell nf = 2*dim*dim + 5 values
+   [strain (dim*dim), stress (dim*dim), pressure = tr(sigma)/3, von Mises, det(I + grad u), det(I + cbar*gamma*I),
+   rho*cbar*(1-cbar)].  cell_out[n_cells][nf] and/or vertex_out[n_vertices][nf] (volume-weighted nodal average);
+   either may be NULL. */
+int glims_cell_fields(glims_ctx* c, double* cell_out, double* vertex_out);
 /* number of kernels this context has launched so far */
 int64_t glims_launch_count(const glims_ctx* c);
 

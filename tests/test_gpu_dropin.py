@@ -115,3 +115,30 @@ def test_brain_variant_agrees_with_dict_parameters(tmp_path):
     # comparison metric of the reference (helper_classes.py:2001-2013) on the concentration sub-function
     ca, cb = a.solution.sub(1, deepcopy=True), b.solution.sub(1, deepcopy=True)
     assert fenics.errornorm(ca, cb) <= 1e-9 * fenics.norm(ca)
+
+
+def test_postprocess_fields_match_numpy(tmp_path):
+    """N2: per-cell strain / stress / pressure / von Mises / Jacobians from the device kernel equal a numpy evaluation
+    of math_linear_elasticity.py:12-46 on the same solution; nodal fields are the volume-weighted averages."""
+    sim = _script(tmp_path, None)
+    sim.init_postprocess(str(tmp_path / "pp"))
+    pp = sim.postprocess
+    mesh, form = sim.mesh, sim.solver.problem.form
+    x = sim.results.get_result(10).get_field().vector().get_local().reshape(-1, 3)
+    G, V = fem.geometry(mesh.coords, mesh.cells)
+    gu = np.einsum("ebi,ebj->eij", x[mesh.cells][:, :, :2], G)
+    eps = 0.5 * (gu + gu.transpose(0, 2, 1))
+    mu, lam = form.table[form.cell_mat, 0], form.table[form.cell_mat, 1]
+    sig = 2 * mu[:, None, None] * eps + (lam * np.trace(eps, axis1=1, axis2=2))[:, None, None] * np.eye(2)
+    s_dev = sig - (np.trace(sig, axis1=1, axis2=2) / 3.0)[:, None, None] * np.eye(2)
+    vm = np.sqrt(1.5 * (s_dev ** 2).sum(axis=(1, 2)))
+    detF = np.linalg.det(np.eye(2)[None] + gu)
+    got = pp.get_stress_tensor(10, cellwise=True).vector().get_local().reshape(-1, 2, 2)
+    assert np.abs(got - sig).max() <= 1e-13 * np.abs(sig).max()
+    assert np.abs(pp.get_van_mises_stress(10, cellwise=True).vector().get_local() - vm).max() <= 1e-13 * vm.max()
+    assert np.abs(pp.get_total_jacobian(10, cellwise=True).vector().get_local() - detF).max() <= 1e-14
+    p_cell = np.trace(sig, axis1=1, axis2=2) / 3.0
+    lumped = np.bincount(mesh.cells.ravel(), weights=np.repeat(V, 3), minlength=mesh.num_vertices())
+    p_node = np.bincount(mesh.cells.ravel(), weights=np.repeat(V * p_cell, 3), minlength=mesh.num_vertices()) / lumped
+    assert np.abs(pp.get_pressure(10).vector().get_local() - p_node).max() <= 1e-12 * np.abs(p_node).max()
+    assert pp.get_displacement_norm(10).vector().get_local().max() > 0
