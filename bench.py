@@ -245,7 +245,7 @@ def main():
         assert rc == 0
         eng.step(1, **opts)
         assert lib.glims_get_state(eng._h, N.as_dp(pin_out)) == 0   # D2H: the step's solution
-        pin_in[:] = pin_out
+        pin_in, pin_out = pin_out, pin_in                           # u_previous <- solution on the host (buffer swap)
     barrier()
     e2e_elapsed = time.perf_counter() - t0
     if world > 1:

@@ -192,7 +192,7 @@ class NonlinearVariationalSolver:
                 raise
             stats = self.last_stats
         self.last_stats = stats
-        u._x[:] = eng.get_state()
+        eng.get_state(out=u._x)
         u._touch()
         # the device did u_previous.assign(solution) already (glims_step); remember what it holds
         self._pushed_version = ((id(u), u.version), None)

@@ -103,7 +103,12 @@ class Engine:
     def set_state(self, x):
         self._vec(self._lib.glims_set_state, "set_state", x)
 
-    def get_state(self):
+    def get_state(self, out=None):
+        """Device -> host copy of the iterate; ``out`` (C-contiguous float64, ndof) is filled in place if given."""
+        if out is not None:
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.ndof
+            self._check(self._lib.glims_get_state(self._h, N.as_dp(out)), "get_state")
+            return out
         return self._vec(self._lib.glims_get_state, "get_state")
 
     def set_prev(self, x):
