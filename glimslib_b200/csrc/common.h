@@ -130,6 +130,7 @@ struct glims_ctx {
     bool first_step_done = false;
     // successive-right-hand-side projection for the constant K_uu (solver.cu: pcg)
     int rec_n = 0, rec_head = 0;
+    void* solver_state = nullptr;   // solver.cu: work-vector pool, projection history, graph cache
     bool have_hist = false;     // x_hist holds the solution two steps back (extrapolated Newton start)
 };
 

@@ -16,8 +16,6 @@ void launch_cell_to_vertex(glims_ctx* c, int nf, const double* q, const double* 
 
 namespace {
 
-struct Pool { std::map<std::string, std::pair<double*, i64>> m; };
-std::map<glims_ctx*, Pool> g_pools;
 struct GraphKey {
     int which, pc; void* amg; void* x; void* r; int bs;
     bool operator<(const GraphKey& o) const {
@@ -25,16 +23,20 @@ struct GraphKey {
     }
 };
 struct PcgGraph { cudaGraphExec_t exec = nullptr; i64 launches = 0; bool failed = false; };
-std::map<glims_ctx*, std::map<GraphKey, PcgGraph>> g_graphs;
-void free_graphs(glims_ctx* c) {
-    for (auto& kv : g_graphs[c]) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    g_graphs.erase(c);
+
+// Everything the host drivers keep per context (no process-global state: contexts may live on different threads)
+struct SolverState {
+    std::map<std::string, std::pair<double*, i64>> pool;     // named device work vectors
+    std::vector<std::vector<double>> rec_hist;               // a[j][k]: coefficient of U_k in the j-th most recent solution
+    std::map<GraphKey, PcgGraph> graphs;                     // captured PCG iterations
+};
+SolverState& state(glims_ctx* c) {
+    if (!c->solver_state) c->solver_state = new SolverState();
+    return *static_cast<SolverState*>(c->solver_state);
 }
-struct RecHist { std::vector<std::vector<double>> a; };   // a[j][k]: coefficient of U_k in the j-th most recent solution
-std::map<glims_ctx*, RecHist> g_rec;
 
 double* ws(glims_ctx* c, const char* name, i64 n) {
-    auto& e = g_pools[c].m[name];
+    auto& e = state(c).pool[name];
     if (e.second < n) {
         if (e.first) cudaFree(e.first);
         GL_CUDA(cudaMalloc(&e.first, sizeof(double) * (n > 0 ? n : 1)));
@@ -43,11 +45,16 @@ double* ws(glims_ctx* c, const char* name, i64 n) {
     }
     return e.first;
 }
+void free_graphs(glims_ctx* c) {
+    for (auto& kv : state(c).graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    state(c).graphs.clear();
+}
 void free_pool(glims_ctx* c) {
-    for (auto& kv : g_pools[c].m) cudaFree(kv.second.first);
-    g_pools.erase(c);
-    g_rec.erase(c);
+    if (!c->solver_state) return;
+    for (auto& kv : state(c).pool) cudaFree(kv.second.first);
     free_graphs(c);
+    delete static_cast<SolverState*>(c->solver_state);
+    c->solver_state = nullptr;
 }
 
 struct EvTimer {           // accumulates device time of bracketed segments on the stream
@@ -122,7 +129,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
             launch_multi_axpy(c, U, nl, c->rec_n, coef, 1.0, x, n);
             launch_multi_axpy(c, AU, nl, c->rec_n, coef, -1.0, r, n);
         }
-        if (c->rec_n == 0) g_rec[c].a.clear();
+        if (c->rec_n == 0) state(c).rec_hist.clear();
         launch_copy(c, r, r0, n);
     }
     launch_dot(c, b, b, n, S_BN);
@@ -165,7 +172,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
         GL_CUDA(cudaMemcpyAsync(c->h_ring, ring, sizeof(double) * 64, cudaMemcpyDeviceToHost, c->stream));
     };
     GraphKey key{which, pc, (void*)c->amg, (void*)x, (void*)r, bs};
-    PcgGraph* G = c->use_graphs ? &g_graphs[c][key] : nullptr;
+    PcgGraph* G = c->use_graphs ? &state(c).graphs[key] : nullptr;
     cudaEvent_t ev[2];
     cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
@@ -214,7 +221,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
                 GL_CUDA(cudaStreamSynchronize(c->stream));
                 for (int k = 0; k < c->rec_n; ++k) acur[k] = c->h_scal[S_GM0 + k];
             }
-            RecHist& H = g_rec[c];
+            auto& Ha = state(c).rec_hist;
             if (c->rec_n >= REC_M) {
                 // Basis full: compress it to an A-orthonormal basis of span{last REC_KEEP-1 solutions, the
                 // projection part of this one}.  U is A-orthonormal, so Gram-Schmidt on the small coefficient
@@ -222,8 +229,8 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
                 const int m = c->rec_n;
                 std::vector<std::vector<double>> cand;
                 cand.push_back(std::vector<double>(acur.begin(), acur.begin() + m));
-                for (size_t j = 0; j < H.a.size() && (int)cand.size() < REC_KEEP; ++j)
-                    cand.push_back(std::vector<double>(H.a[j].begin(), H.a[j].begin() + m));
+                for (size_t j = 0; j < Ha.size() && (int)cand.size() < REC_KEEP; ++j)
+                    cand.push_back(std::vector<double>(Ha[j].begin(), Ha[j].begin() + m));
                 std::vector<std::vector<double>> Q;
                 for (auto v : cand) {
                     double n0 = 0; for (double t : v) n0 += t * t;
@@ -252,8 +259,8 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
                     for (int i = 0; i < kq; ++i) { double d = 0; for (int k = 0; k < m; ++k) d += Q[i][k] * v[k]; o[i] = d; }
                     return o;
                 };
-                for (auto& h : H.a) h = reproject(h);
-                if ((int)H.a.size() > REC_KEEP) H.a.resize(REC_KEEP);
+                for (auto& h : Ha) h = reproject(h);
+                if ((int)Ha.size() > REC_KEEP) Ha.resize(REC_KEEP);
                 acur = reproject(acur);
                 c->rec_n = kq;
             }
@@ -280,8 +287,8 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
                     c->rec_n = slot + 1;
                     acur[slot] = std::sqrt(nn);
                 }
-                H.a.insert(H.a.begin(), acur);            // newest first
-                if ((int)H.a.size() > REC_KEEP) H.a.resize(REC_KEEP);
+                Ha.insert(Ha.begin(), acur);            // newest first
+                if ((int)Ha.size() > REC_KEEP) Ha.resize(REC_KEEP);
             }
         }
         launch_axpy(c, 1.0, xbar, x, n);      // x = x_bar + correction
@@ -437,8 +444,10 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
         if (k == o->max_newton) break;
 
         tm.begin(2);
-        if (o->solver == GLIMS_SOLVER_MONO_GMRES) {
-            launch_bc_matrix(c, GLIMS_ASM_KCC, true);
+        // monolithic update: GMRES(30) on J with block-Jacobi; also the fallback when a block solve breaks down
+        // (e.g. K_cc indefinite for dt*rho > 1, where PCG is not applicable but the reference's GMRES still is)
+        auto mono_update = [&](bool kcc_eliminated) {
+            if (!kcc_eliminated) launch_bc_matrix(c, GLIMS_ASM_KCC, true);
             launch_diag_inverse(c, 0);
             double* rhs = ws(c, "rhs_mono", c->ndof);
             launch_copy(c, c->F, rhs, nr * NB);
@@ -448,23 +457,30 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
             if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "GMRES did not converge");
             s.krylov_its_mono += its;
             launch_axpy(c, 1.0, c->dx, c->x, nr * NB);
+        };
+        if (o->solver == GLIMS_SOLVER_MONO_GMRES) {
+            mono_update(false);
         } else {
             launch_extract(c, c->F, Fu, Fc);
             const bool c_done = fc <= 0.5 * T;
             c_was_done = c_was_done || c_done;
             const bool solve_c = fc > 0.0 && (!c_done || !o->lag_mechanics);
             const bool solve_u_now = c_done || !o->lag_mechanics;
+            bool broke = false, kcc_elim = false;
             if (solve_c && !with_kcc) launch_assemble(c, GLIMS_ASM_KCC, o->asm_kernel);
             if (solve_c) {
+                kcc_elim = true;
                 launch_bc_matrix(c, GLIMS_ASM_KCC, true);
                 launch_diag_inverse(c, 2);
                 launch_scale(c, -1.0, Fc, nr);
                 double res = 0;
                 int its = pcg(c, 2, GLIMS_PC_JACOBI, Fc, dc, o->ksp_rtol, fc, o->ksp_atol, o->max_krylov, &res);
-                if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "PCG on K_cc did not converge");
-                s.krylov_its_c += its;
+                if (its < 0) broke = true; else s.krylov_its_c += its;
             } else launch_zero(c, dc, nr);
-            if (solve_u_now && fu > 0.0) {
+            if (broke) {
+                if (!with_kcc && !solve_c) launch_assemble(c, GLIMS_ASM_KCC, o->asm_kernel);
+                mono_update(kcc_elim);
+            } else if (solve_u_now && fu > 0.0) {
                 // rhs_u = -F_u - K_uc dc
                 if (solve_c) {
                     halo_exchange(c, dc, 1);
@@ -474,9 +490,14 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
                 launch_scale(c, -1.0, Fu, nr * D);
                 double res = 0;
                 int its = pcg(c, 1, o->pc, Fu, du, o->ksp_rtol, fu_scale, o->ksp_atol, o->max_krylov, &res, o->recycle != 0);
-                if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "PCG on K_uu did not converge");
-                s.krylov_its_u += its;
-                launch_insert_add(c, c->x, du, dc, 1.0);
+                if (its < 0) {
+                    // K_uu PCG broke down: take the monolithic update instead (needs the current K_cc)
+                    if (!with_kcc && !solve_c) launch_assemble(c, GLIMS_ASM_KCC, o->asm_kernel);
+                    mono_update(kcc_elim);
+                } else {
+                    s.krylov_its_u += its;
+                    launch_insert_add(c, c->x, du, dc, 1.0);
+                }
             } else launch_insert_add(c, c->x, nullptr, dc, 1.0);
         }
         tm.end(2);

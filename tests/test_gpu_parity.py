@@ -255,3 +255,25 @@ def test_pure_neumann_mechanics_is_reported_not_hung():
     except SolverNotConverged:
         pass
     eng.close()
+
+
+def test_indefinite_concentration_block_falls_back_to_gmres():
+    """dt*rho > 1 makes K_cc = (1 - dt*rho) M + ... indefinite: PCG is not applicable, the reference's GMRES is.
+    The block solver must fall back to the monolithic GMRES update and still match the oracle."""
+    prob, rng = small_problem(2, seed=11, n=10, with_bc=True)
+    prob.mats = fem.Materials.from_E_nu([3e-3, 3e-3, 3e-3], [0.3, 0.3, 0.3], [1e-3, 1e-3, 1e-3], [1.0, 1.0, 1.0], [0.1, 0.1, 0.1])
+    prob.dt = 1.5          # K_cc spectrum at the start: [-2.4e-3, 1.2e-2] (checked with the oracle)
+    prob.f_ext = None
+    bc_u = prob.bc_dofs % 3 != 2
+    prob.bc_dofs, prob.bc_vals = prob.bc_dofs[bc_u], 0.0 * prob.bc_vals[bc_u]
+    x0 = np.zeros(prob.ndof)
+    x0[2::3] = 0.1 + 0.02 * np.cos(3 * prob.coords[:, 0])
+    x_ref, _ = osolver.newton(prob, x0.copy(), x0, linear="lu", rtol=1e-12, atol=1e-14)
+    eng = make_engine(prob)
+    eng.set_prev(x0)
+    eng.set_state(x0)
+    st = eng.step(1, snes_rtol=1e-11, snes_atol=1e-14, ksp_rtol=1e-12, max_krylov=3000)[0]
+    assert st["converged"] == 1
+    x = eng.get_state()
+    assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-7
+    eng.close()
