@@ -18,14 +18,14 @@ SYMBOLS = [
     "glims_set_prev", "glims_get_prev", "glims_ndof", "glims_nnzb", "glims_nslots", "glims_state_dev",
     "glims_stream", "glims_step", "glims_assemble", "glims_get_residual", "glims_export_pattern",
     "glims_export_values", "glims_spmv", "glims_time_kernel", "glims_launch_count", "glims_cell_fields",
-    "glims_nccl_unique_id", "glims_comm_init", "glims_set_halo",
+    "glims_nccl_unique_id", "glims_comm_init", "glims_set_halo", "glims_tile_info", "glims_tile_config",
 ]
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOT_CONVERGED, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5
 ASM_RESIDUAL, ASM_KCONST, ASM_KCC, ASM_JACOBIAN, ASM_ALL = 1, 2, 4, 6, 7
 SOLVER_BLOCK_TRI, SOLVER_MONO_GMRES = 0, 1
 PC_JACOBI, PC_AMG, PC_AMG_FP64 = 0, 1, 2
-ASMK_ATOMIC, ASMK_GATHER, ASMK_SLICE = 0, 1, 2
+ASMK_ATOMIC, ASMK_GATHER, ASMK_SLICE, ASMK_TILE = 0, 1, 2, 3
 
 
 class SolverOpts(C.Structure):
@@ -89,6 +89,8 @@ def load():
         "glims_nccl_unique_id": (i32, [p]),
         "glims_comm_init": (i32, [p, i32, i32, p]),
         "glims_set_halo": (i32, [p, i32, ip, lp, ip, lp]),
+        "glims_tile_info": (i32, [p, lp]),
+        "glims_tile_config": (i32, [p, i32, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

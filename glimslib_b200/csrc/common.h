@@ -95,6 +95,8 @@ struct glims_ctx {
     int sl_max = 0;
     i64 sl_total = 0;
     bool have_slice = false;
+    int tile_nt = 0, tile_chunk = 0;   // 0: GLIMS_TILE_NT / GLIMS_TILE_CH or the defaults (glims_tile_config)
+    void* tile = nullptr;       // tile.cu: TileDev (maps of the fused tile-assembly kernel), built on first use
 
     // matrices (SELL value layout, see vidx)
     double *Kuu = nullptr, *Kuc = nullptr, *Kcc = nullptr;
@@ -143,6 +145,11 @@ void build_slice_map(glims_ctx* c);
 void build_pattern_from_keys(cudaStream_t st, unsigned long long* keys, i64 n_keys, i64 n_rows, SellPattern& P,
                              unsigned long long** ukeys_out);
 void free_pattern(SellPattern& P);
+
+// ---------------- tile.cu
+bool launch_assemble_tile(glims_ctx* c, int what);   // false: maps cannot represent this mesh (caller falls back)
+void tile_free(glims_ctx* c);
+const char* tile_status(glims_ctx* c, long long* info8);
 
 // ---------------- kernels.cu (launch wrappers; all on c->stream)
 void launch_assemble(glims_ctx* c, int what, int variant);

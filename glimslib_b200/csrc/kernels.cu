@@ -945,6 +945,15 @@ static void assemble_dim(glims_ctx* c, int what, int variant) {
     i64 n_own = c->pat.n_rows;
     const bool res = what & GLIMS_ASM_RESIDUAL, kconst = what & GLIMS_ASM_KCONST, kcc = what & GLIMS_ASM_KCC;
     i64 ns = c->pat.n_slots;
+    if (variant == GLIMS_ASMK_TILE) {
+        // fused residual + Jacobian, one CTA per slice; writes every owned row of F and every slot (no zero-fill)
+        if (res && c->halo.active)
+            GL_CUDA(cudaMemsetAsync(c->F + n_own * NB, 0, sizeof(double) * (c->n_v - n_own) * NB, c->stream));
+        if (launch_assemble_tile(c, what)) return;
+        static bool warned = false;
+        if (!warned) { fprintf(stderr, "glims: tile assembly unavailable (%s); using the slice/atomic kernels\n", tile_status(c, nullptr)); warned = true; }
+        variant = GLIMS_ASMK_SLICE;
+    }
     if (res) {
         GL_CUDA(cudaMemsetAsync(c->F, 0, sizeof(double) * c->ndof, c->stream));
     }

@@ -576,6 +576,7 @@ int glims_destroy(glims_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->amg) amg_free(c);
+    tile_free(c);
     free_pool(c);
     auto& p = c->pat;
     for (void* q : {(void*)c->coords, (void*)c->cells, (void*)c->cell_mat, (void*)c->mat, (void*)p.slice_off,
@@ -771,6 +772,26 @@ int glims_cell_fields(glims_ctx* c, double* cell_out, double* vertex_out) {
     API_END
 }
 
+int glims_tile_config(glims_ctx* c, int32_t threads_per_cta, int32_t chunk) {
+    API_BEGIN
+    if (threads_per_cta != 0 && threads_per_cta != 128 && threads_per_cta != 256)
+        throw GlError(GLIMS_ERR_ARG, "glims_tile_config: threads_per_cta must be 0, 128 or 256");
+    if (chunk < 0) throw GlError(GLIMS_ERR_ARG, "glims_tile_config: chunk must be >= 0");
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    tile_free(c);
+    c->tile_nt = threads_per_cta; c->tile_chunk = chunk;
+    API_END
+}
+
+int glims_tile_info(glims_ctx* c, int64_t* info8) {
+    API_BEGIN
+    long long tmp[8] = {0};
+    const char* st = tile_status(c, tmp);
+    if (std::string(st) != "ok") throw GlError(GLIMS_ERR_STATE, std::string("tile maps: ") + st);
+    for (int i = 0; i < 8; ++i) info8[i] = tmp[i];
+    API_END
+}
+
 int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t reps, int32_t do_flush, float* ms_avg) {
     API_BEGIN
     if (!c->have_mat || reps <= 0 || !ms_avg) throw GlError(GLIMS_ERR_ARG, "glims_time_kernel: bad arguments/state");
@@ -784,6 +805,7 @@ int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t rep
             case 2: launch_spmv(c, 1, dx, dy); break;
             case 3: launch_spmv(c, 2, dx, dy); break;
             case 4: launch_assemble(c, GLIMS_ASM_RESIDUAL, variant); break;
+            case 5: launch_assemble(c, GLIMS_ASM_RESIDUAL | GLIMS_ASM_KCC, variant); break;
             default: throw GlError(GLIMS_ERR_ARG, "glims_time_kernel: unknown kernel");
         }
     };

@@ -188,6 +188,18 @@ class Engine:
         self._check(self._lib.glims_time_kernel(self._h, kernel, variant, reps, int(flush_l2), C.byref(ms)), "time_kernel")
         return float(ms.value)
 
+    TILE_INFO = ("max_local_vertices", "max_element_records", "max_entries", "max_items", "max_partial_buffers",
+                 "smem_bytes_per_cta", "map_bytes", "threads_per_cta")
+
+    def tile_info(self):
+        """Statistics of the tile-assembly maps (valid after the first ``assemble(kernel=ASMK_TILE)``)."""
+        info = np.zeros(8, dtype=np.int64)
+        self._check(self._lib.glims_tile_info(self._h, N.as_lp(info)), "tile_info")
+        return dict(zip(self.TILE_INFO, (int(v) for v in info)))
+
+    def tile_config(self, threads_per_cta=0, chunk=0):
+        self._check(self._lib.glims_tile_config(self._h, threads_per_cta, chunk), "tile_config")
+
     @property
     def nnzb(self):
         return int(self._lib.glims_nnzb(self._h))

@@ -50,7 +50,10 @@ enum { GLIMS_PC_JACOBI = 0,          /* (block-)Jacobi on every block */
 /* assembly kernel variant for the Jacobian */
 enum { GLIMS_ASMK_ATOMIC = 0,        /* element-parallel, scatter map + RED.ADD.F64 */
        GLIMS_ASMK_GATHER = 1,        /* row-parallel gather through the transposed scatter map: no atomics, deterministic */
-       GLIMS_ASMK_SLICE = 2          /* gather with the element geometry of each 32-row slice staged in shared memory */ };
+       GLIMS_ASMK_SLICE = 2,         /* gather with the element geometry of each 32-row slice staged in shared memory */
+       GLIMS_ASMK_TILE = 3           /* fused residual+Jacobian, one CTA per 16-row tile: vertices, element gradients and
+                                        contributor lists staged in shared memory, material-free raw sums per slot, residual
+                                        from the same sums; no atomics, deterministic (csrc/tile.h, tile.cu) */ };
 
 typedef struct {
     /* SNES-like controls; defaults mirror DOLFIN's PETScSNESSolver defaults that
@@ -146,7 +149,8 @@ int glims_export_values(glims_ctx* c, double* Kuu, double* Kuc, double* Kcc);
 int glims_spmv(glims_ctx* c, int32_t which, const double* x, double* y);
 /* Average device time (ms, CUDA events on the context stream) of `reps` back-to-back launches of
    one kernel on resident data: kernel 0 = full assembly (residual+Jacobian, `variant` = GLIMS_ASMK_*),
-   1 = monolithic SpMV, 2 = K_uu SpMV, 3 = K_cc SpMV, 4 = residual only. flush_l2 != 0 writes a
+   1 = monolithic SpMV, 2 = K_uu SpMV, 3 = K_cc SpMV, 4 = residual only, 5 = residual + K_cc (the per-Newton-iteration
+   pass of the block-triangular solver). flush_l2 != 0 writes a
    >L2-sized buffer between launches (outside the timed events). */
 int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t reps, int32_t flush_l2,
                       float* ms_avg);
@@ -156,6 +160,14 @@ int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t rep
    rho*cbar*(1-cbar)].  cell_out[n_cells][nf] and/or vertex_out[n_vertices][nf] (volume-weighted nodal average);
    either may be NULL. */
 int glims_cell_fields(glims_ctx* c, double* cell_out, double* vertex_out);
+/* Tile-assembly map statistics (after the first GLIMS_ASMK_TILE assembly): info[0..7] = max local vertices, max element
+   records, max contributor entries, max items, max partial buffers per slice, shared-memory bytes per CTA, device bytes of
+   the maps, threads per CTA.  Returns GLIMS_ERR_STATE when the maps were not built or cannot represent the mesh. */
+int glims_tile_info(glims_ctx* c, int64_t* info8);
+/* Tuning knobs of the tile kernel: threads per CTA (128 or 256; 0 = default 128 / env GLIMS_TILE_NT) and the longest
+   contributor chunk one warp handles before a column is split (0 = default 12 / env GLIMS_TILE_CH).  Drops the maps;
+   they are rebuilt by the next GLIMS_ASMK_TILE assembly. */
+int glims_tile_config(glims_ctx* c, int32_t threads_per_cta, int32_t chunk);
 /* number of kernels this context has launched so far */
 int64_t glims_launch_count(const glims_ctx* c);
 

@@ -67,7 +67,7 @@ def test_mass_is_conserved_without_proliferation(name):
 
 @pytest.mark.parametrize("name", ["C2", "C3"])
 def test_assembly_variants_agree_and_blocks_are_symmetric(name):
-    """atomic == gather == slice at full size (<= 1e-12: summation order differs), and the Dirichlet-eliminated
+    """atomic == gather == slice == tile at full size (<= 1e-12: summation order differs), and the Dirichlet-eliminated
     K_uu, K_cc satisfy x.(A y) == y.(A x) (needed by PCG)."""
     from glimslib_b200 import _native as N
     w = _wl(name)
@@ -78,7 +78,7 @@ def test_assembly_variants_agree_and_blocks_are_symmetric(name):
     ref = None
     xu, yu = rng.standard_normal(eng.n_vertices * d), rng.standard_normal(eng.n_vertices * d)
     xc, yc = rng.standard_normal(eng.n_vertices), rng.standard_normal(eng.n_vertices)
-    for kernel in (N.ASMK_ATOMIC, N.ASMK_GATHER, N.ASMK_SLICE):
+    for kernel in (N.ASMK_ATOMIC, N.ASMK_GATHER, N.ASMK_SLICE, N.ASMK_TILE):
         eng.assemble(what=N.ASM_JACOBIAN, kernel=kernel, apply_bc=2)
         res = (eng.spmv(1, xu), eng.spmv(2, xc), eng.spmv(0, np.ones(eng.ndof)))
         if ref is None:

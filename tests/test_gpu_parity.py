@@ -58,7 +58,7 @@ def relerr(a, b):
 
 
 @pytest.mark.parametrize("d", [2, 3])
-@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
 def test_assembly_matches_oracle(d, kernel):
     """K1/K2: residual and Jacobian values, raw and with DOLFIN-style Dirichlet rows; <= 1e-13 relative."""
     prob, rng = small_problem(d)
@@ -94,11 +94,52 @@ def test_atomic_and_gather_kernels_agree(d):
     eng.set_state(rng.standard_normal(prob.ndof))
     eng.assemble(what=6, kernel=0)
     a = eng.export_blocks()
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3):
         eng.assemble(what=6, kernel=kernel)
         b = eng.export_blocks()
         for p, q in zip(a[2:], b[2:]):
             assert relerr(p, q) < 1e-13
+    eng.close()
+
+
+@pytest.mark.parametrize("d,n", [(2, 40), (3, 12)])
+@pytest.mark.parametrize("nt,chunk", [(128, 12), (256, 8), (128, 5), (256, 100)])
+def test_tile_kernel_all_masks_and_configs(d, n, nt, chunk):
+    """Fused tile kernel (GLIMS_ASMK_TILE): every `what` mask leaves exactly the requested outputs equal to the oracle,
+    for every CTA size / column-split setting (split columns combine partial sums across warps), on a jittered
+    three-tissue mesh with several slices and a ragged last slice; <= 1e-13 relative."""
+    prob, rng = small_problem(d, seed=7, n=n, with_bc=False)
+    if chunk != 12:    # blocky tissue labels: most slots see one material (fast path), interface slots mix
+        cen = prob.coords[prob.cells].mean(axis=1)
+        prob.cell_mat = ((cen[:, 0] > 0.45).astype(np.int32) + (cen[:, 1] > 0.7).astype(np.int32)).astype(np.int32)
+    x, xp = 0.1 * rng.standard_normal(prob.ndof), 0.1 * rng.standard_normal(prob.ndof)
+    eng = make_engine(prob)
+    eng.tile_config(nt, chunk)
+    eng.set_state(x)
+    eng.set_prev(xp)
+    F0, J0 = fem.assemble(prob, x, xp)
+    eng.assemble(what=7, kernel=3)
+    info = eng.tile_info()
+    assert info["threads_per_cta"] == nt and info["smem_bytes_per_cta"] <= 227 * 1024
+    assert relerr(eng.residual(), F0) < 1e-13
+    assert abs(eng.export_jacobian() - J0).max() / abs(J0).max() < 1e-13
+    # a different state: residual-only and residual+K_cc must refresh F (and K_cc) but leave K_uu/K_uc alone
+    x2 = 0.1 * rng.standard_normal(prob.ndof)
+    eng.set_state(x2)
+    F2, J2 = fem.assemble(prob, x2, xp)
+    eng.assemble(what=1, kernel=3)
+    assert relerr(eng.residual(), F2) < 1e-13
+    assert abs(eng.export_jacobian() - J0).max() / abs(J0).max() < 1e-13
+    eng.assemble(what=5, kernel=3)
+    assert relerr(eng.residual(), F2) < 1e-13
+    assert abs(eng.export_jacobian() - J2).max() / abs(J2).max() < 1e-13
+    # deterministic: bitwise identical on repetition
+    Fa = eng.residual().copy()
+    Ka = eng.export_blocks()
+    eng.assemble(what=7, kernel=3)
+    assert np.array_equal(eng.residual(), Fa)
+    for p, q in zip(Ka[2:], eng.export_blocks()[2:]):
+        assert np.array_equal(p, q)
     eng.close()
 
 
