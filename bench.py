@@ -264,10 +264,11 @@ def main():
         ab = algorithmic_bytes(d, n_v, n_c, nnzb)
         for name, kid, variant, key in (("spmv_kuu", 2, 0, "spmv_kuu"), ("spmv_mono", 1, 0, "spmv_mono"),
                                         ("spmv_kcc", 3, 0, "spmv_kcc"),
+                                        ("assembly_full_tile", 0, 3, "assembly_full"),
                                         ("assembly_full_slice", 0, 2, "assembly_full"),
                                         ("assembly_full_gather", 0, 1, "assembly_full"),
                                         ("assembly_full_atomic", 0, 0, "assembly_full"),
-                                        ("residual", 4, 0, "residual")):
+                                        ("residual", 4, 0, "residual"), ("residual_kcc", 5, 0, "residual")):
             ms = eng.time_kernel(kid, variant, reps=10, flush_l2=True)
             gbs = ab[key] / ms / 1e6
             kernels[name] = {"ms": ms, "algorithmic_bytes": ab[key], "achieved_gbs": gbs, "frac": gbs / peak}

@@ -18,7 +18,7 @@ struct TileDev {
     TileItem* items = nullptr;
     uint16_t* ent = nullptr;
     uint16_t* lcol = nullptr;
-    int lv_cap = 0, el_cap = 0, ent_cap = 0, item_cap = 0, sec_cap = 0, w_cap = 0, n_warps = 0, chunk = 0;
+    int lv_cap = 0, el_cap = 0, ent_cap = 0, item_cap = 0, w_cap = 0, n_warps = 0, chunk = 0;
     bool ok = false;
     std::string why;
     size_t map_bytes = 0;
@@ -43,7 +43,6 @@ k_assemble_tile(const TileArgs A, const TileSmem L) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* sv = (double*)(smem + L.off_sv);
     double* rec = (double*)(smem + L.off_rec);
-    double* sec = (double*)(smem + L.off_sec);
     double* fw = (double*)(smem + L.off_fw);
     double* smat = (double*)(smem + L.off_mat);
     uint16_t* sent = (uint16_t*)(smem + L.off_ent);
@@ -77,57 +76,62 @@ k_assemble_tile(const TileArgs A, const TileSmem L) {
         for (int i = tid; i < h.n_items * (int)(sizeof(TileItem) / 4); i += NT) ((unsigned*)sitems)[i] = src[i];
         for (int i = tid; i < A.n_mat * TILE_MAT_STRIDE; i += NT) smat[i] = A.mat[i];
     }
+    // element records are fetched now (registers) so that their latency overlaps the vertex gathers
+    constexpr int NPRE = 384 / NT;
+    unsigned long long tpre[NPRE];
+#pragma unroll
+    for (int q = 0; q < NPRE; ++q) {
+        const int i = tid + q * NT;
+        tpre[q] = i < h.n_el ? __ldg(&A.te[h.e_off + i]) : TILE_NOELEM;
+    }
     // phase 0: local vertices
-    for (int i = tid; i < h.n_lv; i += NT) tile_stage_vertex<D>(A.tv[h.v_off + i], A.coords, A.x, A.xprev, sv + i * VS);
+    for (int i = tid; i < h.n_lv; i += NT) tile_stage_vertex<D>(__ldg(&A.tv[h.v_off + i]), A.coords, A.x, A.xprev, sv + i * VS);
     __syncthreads();
     // phase A: element records (record n_el is the zero record the padding entries point at)
-    for (int i = tid; i <= h.n_el; i += NT)
+#pragma unroll
+    for (int q = 0; q < NPRE; ++q) {
+        const int i = tid + q * NT;
+        if (i <= h.n_el) tile_stage_element<D>(tpre[q], sv, rec + i * REC, emat + i);
+    }
+    for (int i = tid + NPRE * NT; i <= h.n_el; i += NT)
         tile_stage_element<D>(i < h.n_el ? A.te[h.e_off + i] : TILE_NOELEM, sv, rec + i * REC, emat + i);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    // phase B: one item (two columns) per warp and round
+    // phase B: warps loop over the items (two columns, or the two halves of one long column); no barriers
     double Facc[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) Facc[k] = 0.0;
-    const int n_rounds = (h.n_items + NW - 1) / NW;
-    for (int round = 0; round < n_rounds; ++round) {
-        const int idx = round * NW + warp;
-        if (idx < h.n_items) {
-            const TileItem& it = sitems[idx];      // fields are read from shared memory (hh indexes them dynamically)
-            const int kind = it.kind[hh];
-            const int cj = it.col_j[hh];
-            const int sec0 = it.sec_idx[hh], nsec = it.n_sec[hh];
-            const int lc = kind == TILE_NULL ? row : slcol[cj * TR + row];
-            const bool diag = lc == row;
-            double kf[KF];
-            tile_accumulate<D>(rec, emat, smat, sent + it.ent_off, it.L, lane, it.mixed != 0, diag, A.dt, kf);
-            if (kind == TILE_SECONDARY) {
+    for (int idx = warp; idx < h.n_items; idx += NW) {
+        const TileItem& it = sitems[idx];      // fields are read from shared memory (hh indexes col_j dynamically)
+        const int flags = it.flags;
+        const int cj = it.col_j[hh];
+        const int lcw = slcol[cj * TR + row];
+        const int lc = lcw & ((1 << TILE_LCOL_BITS) - 1);
+        const bool diag = lc == row;
+        double kf[KF];
+        tile_accumulate<D>(rec, emat, smat, sent + it.ent_off, it.L, lane, (flags & TILE_MIXED) != 0, lcw >> TILE_LCOL_BITS,
+                           diag, A.dt, kf);
+        bool writer = hh == 0 || !(flags & (TILE_SPLIT | TILE_NULLB));
+        if (flags & TILE_SPLIT) {
 #pragma unroll
-                for (int k = 0; k < KF; ++k) sec[(sec0 * KF + k) * TR + row] = kf[k];
-            } else if (kind != TILE_NULL) {
-                if (kind == TILE_PRIMARY_SPLIT) {
-                    for (int q = 0; q < nsec; ++q) {
-#pragma unroll
-                        for (int k = 0; k < KF; ++k) kf[k] += sec[((sec0 + q) * KF + k) * TR + row];
-                    }
-                }
-                const double* xa = sv + row * VS;
-                const double* xb = sv + lc * VS;
-                const i64 g = sbase + (i64)cj * 32;
-                const int sl = hf * TR + row;
-                if (wkconst) {
-                    if (wkcc) { if (res) tile_finalize<D, true, true, true>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc);
-                                else tile_finalize<D, true, true, false>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc); }
-                    else      { if (res) tile_finalize<D, true, false, true>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc);
-                                else tile_finalize<D, true, false, false>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc); }
-                } else {
-                    if (wkcc) { if (res) tile_finalize<D, false, true, true>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc);
-                                else tile_finalize<D, false, true, false>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc); }
-                    else if (res) tile_finalize<D, false, false, true>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc);
-                }
+            for (int k = 0; k < KF; ++k) kf[k] += __shfl_xor_sync(0xffffffffu, kf[k], 16);
+        }
+        if (writer) {
+            const double* xa = sv + row * VS;
+            const double* xb = sv + lc * VS;
+            const i64 g = sbase + (i64)cj * 32;
+            const int sl = hf * TR + row;
+            if (wkconst) {
+                if (wkcc) { if (res) tile_finalize<D, true, true, true>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc);
+                            else tile_finalize<D, true, true, false>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc); }
+                else      { if (res) tile_finalize<D, true, false, true>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc);
+                            else tile_finalize<D, true, false, false>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc); }
+            } else {
+                if (wkcc) { if (res) tile_finalize<D, false, true, true>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc);
+                            else tile_finalize<D, false, true, false>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc); }
+                else if (res) tile_finalize<D, false, false, true>(kf, diag, A.dt, xa, xb, g, sl, A.Kuu, A.Kuc, A.Kcc, Facc);
             }
         }
-        if (round + 1 < n_rounds) __syncthreads();
     }
     if (res) {
 #pragma unroll
@@ -199,7 +203,7 @@ static TileDev* tile_ensure(glims_ctx* c) {
     t->ok = M.ok; t->why = M.why;
     if (!M.ok) return t;
     t->lv_cap = M.lv_cap; t->el_cap = M.el_cap; t->ent_cap = M.ent_cap; t->item_cap = M.item_cap;
-    t->sec_cap = M.sec_cap; t->w_cap = M.w_cap; t->n_warps = M.n_warps; t->chunk = M.chunk;
+    t->w_cap = M.w_cap; t->n_warps = M.n_warps; t->chunk = M.chunk;
     // pad the entry array so the last slice's 16-byte copies stay inside the allocation
     M.ent.resize(M.ent.size() + 8, 0);
     M.lcol.resize(M.lcol.size() + 8, 0);
@@ -215,7 +219,7 @@ static TileDev* tile_ensure(glims_ctx* c) {
 
 template <int D>
 static bool tile_launch_dim(glims_ctx* c, TileDev* t, int what) {
-    TileSmem L = tile_smem_layout<D>(t->lv_cap, t->el_cap, t->ent_cap, t->item_cap, t->sec_cap, t->w_cap, t->n_warps, c->n_mat);
+    TileSmem L = tile_smem_layout<D>(t->lv_cap, t->el_cap, t->ent_cap, t->item_cap, t->w_cap, t->n_warps, c->n_mat);
     if (L.total > 227 * 1024) { t->ok = false; t->why = "tile: shared-memory footprint exceeds 227 KB"; return false; }
     TileArgs A;
     A.hdr = t->hdr; A.tv = t->tv; A.te = t->te; A.items = t->items; A.ent = t->ent; A.lcol = t->lcol;
@@ -247,9 +251,9 @@ const char* tile_status(glims_ctx* c, long long* info) {
     TileDev* t = (TileDev*)c->tile;
     if (!t) return "not built";
     if (info) {
-        TileSmem L = c->dim == 2 ? tile_smem_layout<2>(t->lv_cap, t->el_cap, t->ent_cap, t->item_cap, t->sec_cap, t->w_cap, t->n_warps, c->n_mat)
-                                 : tile_smem_layout<3>(t->lv_cap, t->el_cap, t->ent_cap, t->item_cap, t->sec_cap, t->w_cap, t->n_warps, c->n_mat);
-        info[0] = t->lv_cap; info[1] = t->el_cap; info[2] = t->ent_cap; info[3] = t->item_cap; info[4] = t->sec_cap;
+        TileSmem L = c->dim == 2 ? tile_smem_layout<2>(t->lv_cap, t->el_cap, t->ent_cap, t->item_cap, t->w_cap, t->n_warps, c->n_mat)
+                                 : tile_smem_layout<3>(t->lv_cap, t->el_cap, t->ent_cap, t->item_cap, t->w_cap, t->n_warps, c->n_mat);
+        info[0] = t->lv_cap; info[1] = t->el_cap; info[2] = t->ent_cap; info[3] = t->item_cap; info[4] = t->chunk;
         info[5] = (long long)L.total; info[6] = (long long)t->map_bytes; info[7] = t->n_warps * 32;
     }
     return t->ok ? "ok" : t->why.c_str();

@@ -8,8 +8,8 @@
 //          coords, u, c, c_prev                                    -- gathered from global memory once
 //   rec  : per touching element sqrt|K|*grad(lambda_a), sqrt|K|, |K|, |K|*sum(c)   (REC doubles, odd stride)
 //   sent : the tile's contributor entries (u16: local element | a<<12 | b<<14), ELL layout [iteration][lane]
-// Phase B: a warp takes one "item" = two SELL columns of the tile (lanes 0-15 / 16-31; lane & 15 = row), or chunks
-// of a long column such as the diagonal.  Every contributor costs 9 shared-memory doubles and 14 FMAs: the raw sums
+// Phase B: a warp takes one "item" = two SELL columns of the tile (lanes 0-15 / 16-31; lane & 15 = row), or the two
+// halves of one long column such as the diagonal (partial sums combined with a shuffle).  Every contributor costs 9 shared-memory doubles and 14 FMAs: the raw sums
 //   S = sum g~a (x) g~b,  t = sum sqrt|K| g~a,  V = sum |K|,  W = sum |K| sum(c)
 // are material-free; the material enters once per slot (chunks in which a lane mixes tissues take a
 // per-contributor path).  The residual is formed from the same sums: F_u = K_uu u + K_uc c, F_c = (K_lin + J_r/2) c
@@ -37,23 +37,25 @@ struct TileHdr {        // one per tile (tile T = rows [16 T, 16 T + 16) = half 
     tl_i64 e_off;       // into te
     tl_i64 ent_off;     // into ent (u16 units, multiple of 8)
     int item_off;       // into items
-    int n_lv;           // local vertices (>= 16)
+    int n_lv;           // local vertices (>= 16, <= 1024)
     int n_el;           // element records incl. bucket padding; record n_el is the all-zero record
-    int n_items;        // incl. null items
+    int n_items;
     int n_ent;          // u16 entries of this tile (multiple of 8)
-    int n_sec;          // partial-sum buffers used by split columns
+    int pad;
 };
-struct TileItem {       // 20 bytes; index h = lane >> 4 selects the half
-    uint16_t col_j[2];  // SELL column handled by each half-warp
+struct TileItem {       // 12 bytes; h = lane >> 4 selects the half-warp
+    uint16_t col_j[2];  // SELL column handled by each half-warp (equal for a split item)
     uint16_t L;         // contributor iterations (max of the two halves; the shorter one is padded)
-    uint16_t mixed;     // a lane mixes materials inside this chunk: per-contributor weights
+    uint8_t flags;      // TILE_MIXED | TILE_SPLIT | TILE_NULLB
+    uint8_t pad;
     uint32_t ent_off;   // offset (u16 units) inside the tile's entry block
-    uint8_t kind[2];    // 0 primary, 1 secondary, 2 primary with secondaries, 3 null
-    uint8_t sec_idx[2]; // secondary: its buffer; primary(2): first buffer
-    uint8_t n_sec[2];   // primary(2): number of buffers
-    uint8_t pad[2];
 };
-enum { TILE_PRIMARY = 0, TILE_SECONDARY = 1, TILE_PRIMARY_SPLIT = 2, TILE_NULL = 3 };
+// MIXED: some lane mixes materials in this column -> per-contributor weights.  SPLIT: both half-warps work on
+// the same (long) column, first / second half of its contributors; the partial sums are combined with a shuffle
+// and half 0 writes.  NULLB: half 1 has no column.
+enum { TILE_MIXED = 1, TILE_SPLIT = 2, TILE_NULLB = 4 };
+// lcol entry of a slot: local vertex of the column (10 bits) | material of the slot's contributors << 10
+constexpr int TILE_LCOL_BITS = 10;
 constexpr unsigned long long TILE_NOELEM = ~0ULL;
 constexpr int TILE_MAT_STRIDE = 6;   // mu, lambda, D, rho, gamma, beta (same table as common.h)
 
@@ -147,7 +149,7 @@ GL_HD void tile_stage_element(unsigned long long rec64, const double* sv, double
 //   Vrho = sum rho |K|,  Wrho = sum rho |K| sum(c),  Mv = m(1+d_ab) sum |K|
 template <int D>
 GL_HD void tile_accumulate(const double* rec, const unsigned char* emat, const double* smat, const uint16_t* ent,
-                           int L, int lane, bool mixed, bool diag, double dt, double (&kf)[TileC<D>::KF]) {
+                           int L, int lane, bool mixed, int slot_mat, bool diag, double dt, double (&kf)[TileC<D>::KF]) {
     constexpr int NB = D + 1, DD = D * D, REC = TileC<D>::REC;
     const double mfac = TileC<D>::mass() * (diag ? 2.0 : 1.0);
     if (!mixed) {
@@ -156,7 +158,6 @@ GL_HD void tile_accumulate(const double* rec, const unsigned char* emat, const d
         for (int k = 0; k < DD; ++k) Sm[k] = 0.0;
 #pragma unroll
         for (int k = 0; k < D; ++k) t[k] = 0.0;
-        int m = 255;
         for (int j = 0; j < L; ++j) {
             const unsigned e = ent[j * 32 + lane];
             const int lel = e & 0xfff;
@@ -175,11 +176,8 @@ GL_HD void tile_accumulate(const double* rec, const unsigned char* emat, const d
             }
             V += r[NB * D + 1];
             W += r[NB * D + 2];
-            const int mm = emat[lel];
-            m = mm < m ? mm : m;
         }
-        if (m == 255) m = 0;
-        const double* mt = smat + m * TILE_MAT_STRIDE;
+        const double* mt = smat + slot_mat * TILE_MAT_STRIDE;
         const double mu = mt[0], lam = mt[1], Dc = mt[2], rho = mt[3], beta = mt[5];
         double tr = 0.0;
 #pragma unroll
@@ -259,20 +257,19 @@ GL_HD void tile_finalize(const double (&kf)[TileC<D>::KF], bool diag, double dt,
 
 // shared-memory carve-up (byte offsets, 16-byte aligned), identical on host and device
 struct TileSmem {
-    int lv_cap, el_cap, ent_cap, item_cap, sec_cap, w_cap, n_warps, n_mat;
-    size_t off_sv, off_rec, off_sec, off_fw, off_mat, off_ent, off_items, off_emat, off_lcol, total;
+    int lv_cap, el_cap, ent_cap, item_cap, w_cap, n_warps, n_mat;
+    size_t off_sv, off_rec, off_fw, off_mat, off_ent, off_items, off_emat, off_lcol, total;
 };
 template <int D>
-inline TileSmem tile_smem_layout(int lv_cap, int el_cap, int ent_cap, int item_cap, int sec_cap, int w_cap, int n_warps,
+inline TileSmem tile_smem_layout(int lv_cap, int el_cap, int ent_cap, int item_cap, int w_cap, int n_warps,
                                  int n_mat) {
     TileSmem s;
-    s.lv_cap = lv_cap; s.el_cap = el_cap; s.ent_cap = ent_cap; s.item_cap = item_cap; s.sec_cap = sec_cap;
+    s.lv_cap = lv_cap; s.el_cap = el_cap; s.ent_cap = ent_cap; s.item_cap = item_cap;
     s.w_cap = w_cap; s.n_warps = n_warps; s.n_mat = n_mat;
     auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
     size_t o = 0;
     s.off_sv = o;    o = up(o + (size_t)lv_cap * TileC<D>::VS * 8);
     s.off_rec = o;   o = up(o + (size_t)(el_cap + 1) * TileC<D>::REC * 8);
-    s.off_sec = o;   o = up(o + (size_t)sec_cap * TileC<D>::KF * TILE_ROWS * 8);
     s.off_fw = o;    o = up(o + (size_t)n_warps * 32 * (D + 1) * 8);   // [warp][half][row][NB]
     s.off_mat = o;   o = up(o + (size_t)n_mat * TILE_MAT_STRIDE * 8);
     s.off_ent = o;   o = up(o + (size_t)ent_cap * 2);
@@ -291,7 +288,7 @@ struct TileMapHost {
     std::vector<TileItem> items;
     std::vector<uint16_t> ent;
     std::vector<uint16_t> lcol;        // [n_slots]
-    int lv_cap = 0, el_cap = 0, ent_cap = 0, item_cap = 0, sec_cap = 0, w_cap = 0, n_warps = 0, chunk = 0;
+    int lv_cap = 0, el_cap = 0, ent_cap = 0, item_cap = 0, w_cap = 0, n_warps = 0, chunk = 0;
     bool ok = false;                   // false: some tile exceeds the 12-bit local index space
     std::string why;
 };

@@ -15,7 +15,7 @@ struct Chunk {       // per worker thread: concatenated outputs of a contiguous 
     std::vector<unsigned long long> te;
     std::vector<TileItem> items;
     std::vector<uint16_t> ent;
-    int lv_cap = 0, el_cap = 0, ent_cap = 0, item_cap = 0, sec_cap = 0;
+    int lv_cap = 0, el_cap = 0, ent_cap = 0, item_cap = 0;
     bool ok = true;
     std::string why;
 };
@@ -28,8 +28,6 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
     std::vector<int> elems, lverts, bucket_of, pos_of;
     std::vector<std::vector<uint16_t>> lists;     // [j*TR + row] contributor entries
     std::vector<std::vector<unsigned char>> lmats;
-    struct Part { int j, lo, hi, part, nparts; bool mixed; };
-    std::vector<Part> parts;
     for (int T = T0; T < T1; ++T) {
         TileHdr h;
         std::memset(&h, 0, sizeof h);
@@ -51,17 +49,22 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
         // emptiest candidate so the buckets stay balanced; position = i*16 + bucket.
         bucket_of.assign(ne, 0);
         int cnt[TR] = {0};
+        const int target = (ne + TR - 1) / TR + 1;
         for (int i = 0; i < ne; ++i) {
-            int best = -1;
+            // prefer the smallest own row (translation-consistent on structured meshes: lanes reading "the same"
+            // element of their own neighbourhood then hit distinct banks); overflow goes to the emptiest own row
+            int first = -1, best = -1;
             for (int a = 0; a < nb; ++a) {
                 int v = cells[(tl_i64)elems[i] * nb + a];
                 if (v >= r0 && v < r0 + nr) {
                     int m = v - r0;
+                    if (first < 0 || m < first) first = m;
                     if (best < 0 || cnt[m] < cnt[best]) best = m;
                 }
             }
-            bucket_of[i] = best;
-            cnt[best]++;
+            const int pick = cnt[first] < target ? first : best;
+            bucket_of[i] = pick;
+            cnt[pick]++;
         }
         int mxb = 0;
         for (int m = 0; m < TR; ++m) mxb = std::max(mxb, cnt[m]);
@@ -106,6 +109,7 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
             out.te[h.e_off + pos_of[i]] = r;
         }
         h.n_el = n_el;
+        if (n_lv > (1 << TILE_LCOL_BITS)) { out.ok = false; out.why = "a tile references more than 1024 vertices"; return; }
         // contributor lists per slot, and the local column of every slot (padding slots: own row)
         lists.assign((size_t)w * TR, std::vector<uint16_t>());
         lmats.assign((size_t)w * TR, std::vector<unsigned char>());
@@ -129,81 +133,54 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
                 }
             }
         }
-        // parts: every column, long ones split into chunks of <= chunk iterations
-        parts.clear();
+        // columns: length, mixed-material flag, slot material (stored in the high bits of lcol)
+        struct Col { int j, L; bool mixed, split; };
+        std::vector<Col> cols;
         for (int j = 0; j < w; ++j) {
-            int Lmax = 0;
-            for (int l = 0; l < TR; ++l) Lmax = std::max(Lmax, (int)lists[(size_t)j * TR + l].size());
-            int np = std::max(1, (Lmax + chunk - 1) / chunk);
-            int step = (Lmax + np - 1) / np;
-            for (int p = 0; p < np; ++p) {
-                Part P{j, p * step, std::min(Lmax, (p + 1) * step), p, np, false};
-                for (int l = 0; l < TR && !P.mixed; ++l) {
-                    auto& lm = lmats[(size_t)j * TR + l];
-                    int m0 = -1;
-                    for (int q = P.lo; q < P.hi && q < (int)lm.size(); ++q) {
-                        if (m0 < 0) m0 = lm[q];
-                        else if (lm[q] != m0) { P.mixed = true; break; }
-                    }
-                }
-                parts.push_back(P);
+            Col C{j, 0, false, false};
+            for (int l = 0; l < TR; ++l) {
+                auto& lm = lmats[(size_t)j * TR + l];
+                C.L = std::max(C.L, (int)lm.size());
+                int m0 = lm.empty() ? 0 : lm[0];
+                for (unsigned char m : lm) if (m != m0) C.mixed = true;
+                lcol[base + (tl_i64)j * 32 + l] |= (uint16_t)(m0 << TILE_LCOL_BITS);
             }
+            C.split = C.L > chunk;
+            cols.push_back(C);
         }
-        // order of the half-items: secondaries, plain primaries (longest first, so paired halves have similar
-        // lengths), split primaries -- those must start in a later round than the last secondary.
-        std::vector<int> order;          // indices into parts, -1 = null half
-        for (int i = 0; i < (int)parts.size(); ++i) if (parts[i].part > 0) order.push_back(i);
-        const int n_secondary = (int)order.size();
-        if (n_secondary > 255) { out.ok = false; out.why = "too many split columns in one tile"; return; }
-        std::vector<int> first_sec(w, -1);
-        for (int q = 0; q < n_secondary; ++q) { int j = parts[order[q]].j; if (first_sec[j] < 0) first_sec[j] = q; }
-        {
-            std::vector<int> plain;
-            for (int i = 0; i < (int)parts.size(); ++i) if (parts[i].part == 0 && parts[i].nparts == 1) plain.push_back(i);
-            std::stable_sort(plain.begin(), plain.end(), [&](int a, int b) { return parts[a].hi - parts[a].lo > parts[b].hi - parts[b].lo; });
-            order.insert(order.end(), plain.begin(), plain.end());
+        // items: a split column takes a whole warp (first / second half of its contributors per half-warp);
+        // the others are paired by decreasing length so that the two halves of a warp have similar trip counts.
+        std::vector<int> plain;
+        for (auto& C : cols) if (!C.split) plain.push_back(C.j);
+        std::stable_sort(plain.begin(), plain.end(), [&](int a, int b) { return cols[a].L > cols[b].L; });
+        struct Item { int jA, jB, L; bool split; };
+        std::vector<Item> its;
+        for (auto& C : cols) if (C.split) its.push_back(Item{C.j, C.j, (C.L + 1) / 2, true});
+        for (size_t q = 0; q < plain.size(); q += 2) {
+            int jA = plain[q], jB = q + 1 < plain.size() ? plain[q + 1] : -1;
+            its.push_back(Item{jA, jB, std::max(cols[jA].L, jB >= 0 ? cols[jB].L : 0), false});
         }
-        bool any_split = false;
-        for (auto& P : parts) any_split |= (P.part == 0 && P.nparts > 1);
-        if (any_split) {
-            const int last_sec_round = ((n_secondary - 1) / 2) / n_warps;
-            while (((int)order.size() / 2) / n_warps <= last_sec_round) order.push_back(-1);
-            for (int i = 0; i < (int)parts.size(); ++i) if (parts[i].part == 0 && parts[i].nparts > 1) order.push_back(i);
-        }
-        if (order.size() % 2) order.push_back(-1);
+        std::stable_sort(its.begin(), its.end(), [](const Item& a, const Item& b) { return a.L > b.L; });
         h.item_off = (int)out.items.size();
         h.ent_off = (tl_i64)out.ent.size();
-        for (size_t q = 0; q < order.size(); q += 2) {
+        for (auto& I : its) {
             TileItem it;
             std::memset(&it, 0, sizeof it);
-            int L = 0;
-            for (int hh = 0; hh < 2; ++hh) {
-                const int pi = order[q + hh];
-                if (pi < 0) { it.kind[hh] = TILE_NULL; continue; }
-                const Part& P = parts[pi];
-                it.col_j[hh] = (uint16_t)P.j;
-                L = std::max(L, P.hi - P.lo);
-                if (P.mixed) it.mixed = 1;
-                if (P.part > 0) {
-                    it.kind[hh] = TILE_SECONDARY;
-                    // buffer index = position among the secondaries (they lead `order`)
-                    it.sec_idx[hh] = (uint8_t)(q + hh);
-                } else if (P.nparts > 1) {
-                    it.kind[hh] = TILE_PRIMARY_SPLIT;
-                    it.sec_idx[hh] = (uint8_t)first_sec[P.j];
-                    it.n_sec[hh] = (uint8_t)(P.nparts - 1);
-                } else it.kind[hh] = TILE_PRIMARY;
-            }
-            it.L = (uint16_t)L;
+            it.col_j[0] = (uint16_t)I.jA;
+            it.col_j[1] = (uint16_t)(I.jB >= 0 ? I.jB : I.jA);
+            it.L = (uint16_t)I.L;
+            it.flags = (uint8_t)((cols[I.jA].mixed || (I.jB >= 0 && cols[I.jB].mixed) ? TILE_MIXED : 0) |
+                                 (I.split ? TILE_SPLIT : 0) | (I.jB < 0 ? TILE_NULLB : 0));
             it.ent_off = (uint32_t)(out.ent.size() - (size_t)h.ent_off);
-            for (int k = 0; k < L; ++k)
+            for (int k = 0; k < I.L; ++k)
                 for (int lane = 0; lane < 32; ++lane) {
-                    const int pi = order[q + (lane >> 4)];
+                    const int hh = lane >> 4;
+                    const int j = hh == 0 ? I.jA : I.jB;
                     uint16_t e = (uint16_t)n_el;                 // sentinel: zero record, a = b = 0
-                    if (pi >= 0) {
-                        const Part& P = parts[pi];
-                        auto& li = lists[(size_t)P.j * TR + (lane & 15)];
-                        if (P.lo + k < P.hi && P.lo + k < (int)li.size()) e = li[P.lo + k];
+                    if (j >= 0) {
+                        auto& li = lists[(size_t)j * TR + (lane & 15)];
+                        const int q = I.split ? hh * I.L + k : k;
+                        if (q < (int)li.size()) e = li[q];
                     }
                     out.ent.push_back(e);
                 }
@@ -212,13 +189,11 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
         while (out.ent.size() % 8) out.ent.push_back((uint16_t)n_el);
         h.n_items = (int)out.items.size() - h.item_off;
         h.n_ent = (int)(out.ent.size() - (size_t)h.ent_off);
-        h.n_sec = n_secondary;
         out.hdr.push_back(h);
         out.lv_cap = std::max(out.lv_cap, n_lv);
         out.el_cap = std::max(out.el_cap, n_el);
         out.ent_cap = std::max(out.ent_cap, h.n_ent);
         out.item_cap = std::max(out.item_cap, h.n_items);
-        out.sec_cap = std::max(out.sec_cap, n_secondary);
     }
 }
 
@@ -254,7 +229,7 @@ void tile_build_map(int dim, tl_i64 n_c, const int* cells, const int* cell_mat, 
     out.w_cap = 0;
     for (int S = 0; S < n_slices; ++S) out.w_cap = std::max(out.w_cap, slice_w[S]);
     out.hdr.clear(); out.tv.clear(); out.te.clear(); out.items.clear(); out.ent.clear();
-    out.lv_cap = out.el_cap = out.ent_cap = out.item_cap = out.sec_cap = 0;
+    out.lv_cap = out.el_cap = out.ent_cap = out.item_cap = 0;
     for (auto& c : chunks) {
         if (!c.ok) { out.ok = false; out.why = c.why; return; }
         const tl_i64 bv = (tl_i64)out.tv.size(), be = (tl_i64)out.te.size(), bent = (tl_i64)out.ent.size();
@@ -269,7 +244,6 @@ void tile_build_map(int dim, tl_i64 n_c, const int* cells, const int* cell_mat, 
         out.ent.insert(out.ent.end(), c.ent.begin(), c.ent.end());
         out.lv_cap = std::max(out.lv_cap, c.lv_cap); out.el_cap = std::max(out.el_cap, c.el_cap);
         out.ent_cap = std::max(out.ent_cap, c.ent_cap); out.item_cap = std::max(out.item_cap, c.item_cap);
-        out.sec_cap = std::max(out.sec_cap, c.sec_cap);
         c = Chunk();
     }
 }

@@ -20,14 +20,13 @@ int emulate(const TileMapHost& M, int n_rows, int n_slices, const i64* slice_off
             const double* fext, double* Kuu, double* Kuc, double* Kcc, double* F) {
     constexpr int NB = D + 1, REC = TileC<D>::REC, VS = TileC<D>::VS, KF = TileC<D>::KF, TR = TILE_ROWS;
     const int NW = M.n_warps;
-    TileSmem L = tile_smem_layout<D>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.sec_cap, M.w_cap, NW, n_mat);
+    TileSmem L = tile_smem_layout<D>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.w_cap, NW, n_mat);
     std::vector<unsigned char> smem(L.total);
     for (int T = 0; T < 2 * n_slices; ++T) {
         const int S = T >> 1, hf = T & 1;
         std::fill(smem.begin(), smem.end(), 0xCD);     // poison: reading anything unstaged shows up as garbage
         double* sv = (double*)(smem.data() + L.off_sv);
         double* rec = (double*)(smem.data() + L.off_rec);
-        double* sec = (double*)(smem.data() + L.off_sec);
         double* fw = (double*)(smem.data() + L.off_fw);
         double* smat = (double*)(smem.data() + L.off_mat);
         uint16_t* sent = (uint16_t*)(smem.data() + L.off_ent);
@@ -35,7 +34,7 @@ int emulate(const TileMapHost& M, int n_rows, int n_slices, const i64* slice_off
         unsigned char* emat = smem.data() + L.off_emat;
         uint16_t* slcol = (uint16_t*)(smem.data() + L.off_lcol);
         const TileHdr h = M.hdr[T];
-        if (h.n_lv > L.lv_cap || h.n_el > L.el_cap || h.n_ent > L.ent_cap || h.n_items > L.item_cap || h.n_sec > L.sec_cap) return -10;
+        if (h.n_lv > L.lv_cap || h.n_el > L.el_cap || h.n_ent > L.ent_cap || h.n_items > L.item_cap) return -10;
         if (slice_w[S] > L.w_cap) return -15;
         std::memcpy(sent, M.ent.data() + h.ent_off, (size_t)h.n_ent * 2);
         std::memcpy(sitems, M.items.data() + h.item_off, (size_t)h.n_items * sizeof(TileItem));
@@ -46,43 +45,37 @@ int emulate(const TileMapHost& M, int n_rows, int n_slices, const i64* slice_off
         for (int i = 0; i < h.n_lv; ++i) tile_stage_vertex<D>(M.tv[h.v_off + i], coords, x, xprev, sv + i * VS);
         for (int i = 0; i <= h.n_el; ++i)
             tile_stage_element<D>(i < h.n_el ? M.te[h.e_off + i] : TILE_NOELEM, sv, rec + i * REC, emat + i);
-        const int n_rounds = (h.n_items + NW - 1) / NW;
-        std::vector<int> sec_round(h.n_sec + 1, -1);
         std::vector<double> Facc((size_t)NW * 32 * NB, 0.0);
-        for (int round = 0; round < n_rounds; ++round)
-            for (int warp = 0; warp < NW; ++warp) {
-                const int idx = round * NW + warp;
-                if (idx >= h.n_items) continue;
-                const TileItem it = sitems[idx];
-                for (int hh = 0; hh < 2; ++hh) {
-                    if (it.kind[hh] == TILE_NULL) continue;
-                    if (it.col_j[hh] >= slice_w[S]) return -11;
-                    if (it.kind[hh] == TILE_SECONDARY) { if (it.sec_idx[hh] >= h.n_sec) return -12; sec_round[it.sec_idx[hh]] = round; }
-                    if (it.kind[hh] == TILE_PRIMARY_SPLIT)
-                        for (int q = 0; q < it.n_sec[hh]; ++q)
-                            if (sec_round[it.sec_idx[hh] + q] < 0 || sec_round[it.sec_idx[hh] + q] >= round) return -13;
-                }
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int hh = lane >> 4, row = lane & 15;
-                    const int kind = it.kind[hh], cj = it.col_j[hh];
-                    const int lc = kind == TILE_NULL ? row : slcol[cj * TR + row];
-                    if (lc >= h.n_lv) return -14;
-                    const bool diag = lc == row;
-                    double kf[KF];
-                    tile_accumulate<D>(rec, emat, smat, sent + it.ent_off, it.L, lane, it.mixed != 0, diag, dt, kf);
-                    if (kind == TILE_NULL) continue;
-                    if (kind == TILE_SECONDARY) {
-                        for (int k = 0; k < KF; ++k) sec[((size_t)it.sec_idx[hh] * KF + k) * TR + row] = kf[k];
-                        continue;
-                    }
-                    if (kind == TILE_PRIMARY_SPLIT)
-                        for (int q = 0; q < it.n_sec[hh]; ++q)
-                            for (int k = 0; k < KF; ++k) kf[k] += sec[((size_t)(it.sec_idx[hh] + q) * KF + k) * TR + row];
-                    double (&fa)[NB] = *reinterpret_cast<double (*)[NB]>(&Facc[((size_t)warp * 32 + lane) * NB]);
-                    tile_finalize<D, true, true, true>(kf, diag, dt, sv + row * VS, sv + lc * VS, sbase + (i64)cj * 32,
-                                                       hf * TR + row, Kuu, Kuc, Kcc, fa);
-                }
+        for (int idx = 0; idx < h.n_items; ++idx) {
+            const int warp = idx % NW;
+            const TileItem it = sitems[idx];
+            double kfs[32][KF];
+            int lcs[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                const int hh = lane >> 4, row = lane & 15;
+                const int cj = it.col_j[hh];
+                if (cj >= slice_w[S]) return -11;
+                const int lcw = slcol[cj * TR + row];
+                const int lc = lcw & ((1 << TILE_LCOL_BITS) - 1);
+                if (lc >= h.n_lv) return -14;
+                lcs[lane] = lc;
+                tile_accumulate<D>(rec, emat, smat, sent + it.ent_off, it.L, lane, (it.flags & TILE_MIXED) != 0,
+                                   lcw >> TILE_LCOL_BITS, lc == row, dt, kfs[lane]);
             }
+            if (it.flags & TILE_SPLIT) {
+                if (it.col_j[0] != it.col_j[1]) return -12;
+                for (int lane = 0; lane < 16; ++lane)
+                    for (int k = 0; k < KF; ++k) { double s2 = kfs[lane][k] + kfs[lane + 16][k]; kfs[lane][k] = s2; kfs[lane + 16][k] = s2; }
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                const int hh = lane >> 4, row = lane & 15;
+                const bool writer = hh == 0 || !(it.flags & (TILE_SPLIT | TILE_NULLB));
+                if (!writer) continue;
+                double (&fa)[NB] = *reinterpret_cast<double (*)[NB]>(&Facc[((size_t)warp * 32 + lane) * NB]);
+                tile_finalize<D, true, true, true>(kfs[lane], lcs[lane] == row, dt, sv + row * VS, sv + lcs[lane] * VS,
+                                                   sbase + (i64)it.col_j[hh] * 32, hf * TR + row, Kuu, Kuc, Kcc, fa);
+            }
+        }
         for (size_t t = 0; t < Facc.size(); ++t) fw[t] = Facc[t];
         for (int t = 0; t < TR * NB; ++t) {
             const int r = T * TR + t / NB;
@@ -167,13 +160,13 @@ extern "C" int tile_emu_assemble(int dim, i64 n_v, i64 n_rows, const double* coo
         }
     }
     if (info) {
-        TileSmem L = dim == 2 ? tile_smem_layout<2>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.sec_cap, M.w_cap, n_warps, n_mat)
-                              : tile_smem_layout<3>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.sec_cap, M.w_cap, n_warps, n_mat);
-        info[0] = M.lv_cap; info[1] = M.el_cap; info[2] = M.ent_cap; info[3] = M.item_cap; info[4] = M.sec_cap;
+        TileSmem L = dim == 2 ? tile_smem_layout<2>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.w_cap, n_warps, n_mat)
+                              : tile_smem_layout<3>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.w_cap, n_warps, n_mat);
+        info[0] = M.lv_cap; info[1] = M.el_cap; info[2] = M.ent_cap; info[3] = M.item_cap; info[4] = 0; for (auto& it : M.items) if (it.flags & TILE_SPLIT) info[4]++;
         info[5] = (i64)L.total; info[6] = bad; info[7] = (i64)M.ent.size();
         if (getenv("TILE_EMU_STATS")) {
             std::vector<int> hel(64, 0), hent(64, 0), hlv(64, 0), hsec(16, 0), hit(64, 0);
-            for (auto& h : M.hdr) { hel[std::min(63, h.n_el / 16)]++; hent[std::min(63, h.n_ent / 256)]++; hlv[std::min(63, h.n_lv / 16)]++; hsec[std::min(15, h.n_sec)]++; hit[std::min(63, h.n_items)]++; }
+            for (auto& h : M.hdr) { hel[std::min(63, h.n_el / 16)]++; hent[std::min(63, h.n_ent / 256)]++; hlv[std::min(63, h.n_lv / 16)]++; hit[std::min(63, h.n_items)]++; }
             fprintf(stderr, "n_el/32 hist:"); for (int i = 0; i < 64; ++i) if (hel[i]) fprintf(stderr, " %d:%d", i * 16, hel[i]);
             fprintf(stderr, "\nn_ent/256 hist:"); for (int i = 0; i < 64; ++i) if (hent[i]) fprintf(stderr, " %d:%d", i * 256, hent[i]);
             fprintf(stderr, "\nn_lv/16 hist:"); for (int i = 0; i < 64; ++i) if (hlv[i]) fprintf(stderr, " %d:%d", i * 16, hlv[i]);
