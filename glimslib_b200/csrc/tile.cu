@@ -39,7 +39,8 @@ struct TileArgs {
 template <int D, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_assemble_tile(const TileArgs A, const TileSmem L) {
-    constexpr int NB = D + 1, REC = TileC<D>::REC, VS = TileC<D>::VS, KF = TileC<D>::KF, NW = NT / 32, TR = TILE_ROWS;
+    constexpr int NB = D + 1, VS = TileC<D>::VS, KF = TileC<D>::KF, NW = NT / 32, TR = TILE_ROWS;
+    const int NE = L.ne;
     extern __shared__ __align__(16) unsigned char smem[];
     double* sv = (double*)(smem + L.off_sv);
     double* rec = (double*)(smem + L.off_rec);
@@ -77,7 +78,7 @@ k_assemble_tile(const TileArgs A, const TileSmem L) {
         for (int i = tid; i < A.n_mat * TILE_MAT_STRIDE; i += NT) smat[i] = A.mat[i];
     }
     // element records are fetched now (registers) so that their latency overlaps the vertex gathers
-    constexpr int NPRE = 384 / NT;
+    constexpr int NPRE = 512 / NT;
     unsigned long long tpre[NPRE];
 #pragma unroll
     for (int q = 0; q < NPRE; ++q) {
@@ -87,14 +88,14 @@ k_assemble_tile(const TileArgs A, const TileSmem L) {
     // phase 0: local vertices
     for (int i = tid; i < h.n_lv; i += NT) tile_stage_vertex<D>(__ldg(&A.tv[h.v_off + i]), A.coords, A.x, A.xprev, sv + i * VS);
     __syncthreads();
-    // phase A: element records (record n_el is the zero record the padding entries point at)
+    // phase A: element records (records n_el .. n_el+15 are the zero records the padding entries point at)
 #pragma unroll
     for (int q = 0; q < NPRE; ++q) {
         const int i = tid + q * NT;
-        if (i <= h.n_el) tile_stage_element<D>(tpre[q], sv, rec + i * REC, emat + i);
+        if (i < h.n_el + TR) tile_stage_element<D>(tpre[q], sv, rec, NE, i, emat + i);
     }
-    for (int i = tid + NPRE * NT; i <= h.n_el; i += NT)
-        tile_stage_element<D>(i < h.n_el ? A.te[h.e_off + i] : TILE_NOELEM, sv, rec + i * REC, emat + i);
+    for (int i = tid + NPRE * NT; i < h.n_el + TR; i += NT)
+        tile_stage_element<D>(i < h.n_el ? A.te[h.e_off + i] : TILE_NOELEM, sv, rec, NE, i, emat + i);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     // phase B: warps loop over the items (two columns, or the two halves of one long column); no barriers
@@ -109,7 +110,7 @@ k_assemble_tile(const TileArgs A, const TileSmem L) {
         const int lc = lcw & ((1 << TILE_LCOL_BITS) - 1);
         const bool diag = lc == row;
         double kf[KF];
-        tile_accumulate<D>(rec, emat, smat, sent + it.ent_off, it.L, lane, (flags & TILE_MIXED) != 0, lcw >> TILE_LCOL_BITS,
+        tile_accumulate<D>(rec, NE, emat, smat, sent + it.ent_off, it.L, lane, (flags & TILE_MIXED) != 0, lcw >> TILE_LCOL_BITS,
                            diag, A.dt, kf);
         bool writer = hh == 0 || !(flags & (TILE_SPLIT | TILE_NULLB));
         if (flags & TILE_SPLIT) {

@@ -6,7 +6,8 @@
 // One CTA owns one tile = 16 consecutive block rows (half a SELL-32 slice).  Shared memory holds
 //   sv   : the tile's local vertices (own 16 rows first, then every other vertex of a touching element):
 //          coords, u, c, c_prev                                    -- gathered from global memory once
-//   rec  : per touching element sqrt|K|*grad(lambda_a), sqrt|K|, |K|, |K|*sum(c)   (REC doubles, odd stride)
+//   rec  : per touching element sqrt|K|*grad(lambda_a), sqrt|K|, |K|, |K|*sum(c); structure of arrays
+//          [a][element][3] + [3][element] so that the bank of an access depends on (element mod 16) only
 //   sent : the tile's contributor entries (u16: local element | a<<12 | b<<14), ELL layout [iteration][lane]
 // Phase B: a warp takes one "item" = two SELL columns of the tile (lanes 0-15 / 16-31; lane & 15 = row), or the two
 // halves of one long column such as the diagonal (partial sums combined with a shuffle).  Every contributor costs 9 shared-memory doubles and 14 FMAs: the raw sums
@@ -38,7 +39,7 @@ struct TileHdr {        // one per tile (tile T = rows [16 T, 16 T + 16) = half 
     tl_i64 ent_off;     // into ent (u16 units, multiple of 8)
     int item_off;       // into items
     int n_lv;           // local vertices (>= 16, <= 1024)
-    int n_el;           // element records incl. bucket padding; record n_el is the all-zero record
+    int n_el;           // element records incl. bucket padding; records n_el .. n_el+15 are all-zero (padding entries)
     int n_items;
     int n_ent;          // u16 entries of this tile (multiple of 8)
     int pad;
@@ -62,7 +63,8 @@ constexpr int TILE_MAT_STRIDE = 6;   // mu, lambda, D, rho, gamma, beta (same ta
 template <int D> struct TileC {
     static constexpr int NB = D + 1;
     static constexpr int DD = D * D;
-    static constexpr int REC = NB * D + 3;     // 15 / 9: odd => conflict-free for distinct (index mod 16)
+    static constexpr int GS = 3;               // doubles per gradient slot (odd: distinct (element mod 16) => distinct banks)
+    static constexpr int REC = NB * GS + 3;    // doubles per element: NB gradient slots + sqrt|K|, |K|, |K| sum(c)
     static constexpr int VS = 2 * D + 3;       // coords, u, c, c_prev (+1 pad): 9 / 7, odd
     static constexpr int KF = DD + D + 4;      // K_uu, K_uc, kl, Vrho, Wrho, Mv
     static constexpr double mass() { return D == 2 ? 1.0 / 12.0 : 1.0 / 20.0; }
@@ -112,13 +114,19 @@ GL_HD void tile_geometry(const double (&X)[4][3], double (&g)[4][3], double& vol
     vol = fabs(det) * (1.0 / 6.0);
 }
 
+// Element records in shared memory, structure of arrays over NE (a multiple of 16) element positions:
+//   gradient a of element i at rec[(a*NE + i)*GS + k];  sqrt|K|, |K|, |K|*sum(c) at rec[NB*NE*GS + q*NE + i].
 // te record: 4 x 12-bit local vertex | material << 48
 template <int D>
-GL_HD void tile_stage_element(unsigned long long rec64, const double* sv, double* o, unsigned char* emat) {
-    constexpr int NB = D + 1, REC = TileC<D>::REC, VS = TileC<D>::VS;
+GL_HD void tile_stage_element(unsigned long long rec64, const double* sv, double* rec, int NE, int i, unsigned char* emat) {
+    constexpr int NB = D + 1, GS = TileC<D>::GS, VS = TileC<D>::VS;
+    double* sc = rec + NB * NE * GS + i;
     if (rec64 == TILE_NOELEM) {
 #pragma unroll
-        for (int k = 0; k < REC; ++k) o[k] = 0.0;
+        for (int a = 0; a < NB; ++a)
+#pragma unroll
+            for (int k = 0; k < D; ++k) rec[(a * NE + i) * GS + k] = 0.0;
+        sc[0] = 0.0; sc[NE] = 0.0; sc[2 * NE] = 0.0;
         *emat = 255;
         return;
     }
@@ -136,10 +144,10 @@ GL_HD void tile_stage_element(unsigned long long rec64, const double* sv, double
 #pragma unroll
     for (int a = 0; a < NB; ++a)
 #pragma unroll
-        for (int k = 0; k < D; ++k) o[a * D + k] = sq * g[a][k];
-    o[NB * D] = sq;
-    o[NB * D + 1] = vol;
-    o[NB * D + 2] = vol * S;
+        for (int k = 0; k < D; ++k) rec[(a * NE + i) * GS + k] = sq * g[a][k];
+    sc[0] = sq;
+    sc[NE] = vol;
+    sc[2 * NE] = vol * S;
     *emat = (unsigned char)((rec64 >> 48) & 0xffULL);
 }
 
@@ -148,9 +156,10 @@ GL_HD void tile_stage_element(unsigned long long rec64, const double* sv, double
 //   kl   = m(1+d_ab) sum (1 - dt rho)|K| + dt sum D |K| g_a.g_b      (linear part of K_cc)
 //   Vrho = sum rho |K|,  Wrho = sum rho |K| sum(c),  Mv = m(1+d_ab) sum |K|
 template <int D>
-GL_HD void tile_accumulate(const double* rec, const unsigned char* emat, const double* smat, const uint16_t* ent,
+GL_HD void tile_accumulate(const double* rec, int NE, const unsigned char* emat, const double* smat, const uint16_t* ent,
                            int L, int lane, bool mixed, int slot_mat, bool diag, double dt, double (&kf)[TileC<D>::KF]) {
-    constexpr int NB = D + 1, DD = D * D, REC = TileC<D>::REC;
+    constexpr int NB = D + 1, DD = D * D, GS = TileC<D>::GS;
+    const double* scal = rec + NB * NE * GS;
     const double mfac = TileC<D>::mass() * (diag ? 2.0 : 1.0);
     if (!mixed) {
         double Sm[DD], t[D], V = 0.0, W = 0.0;
@@ -161,21 +170,20 @@ GL_HD void tile_accumulate(const double* rec, const unsigned char* emat, const d
         for (int j = 0; j < L; ++j) {
             const unsigned e = ent[j * 32 + lane];
             const int lel = e & 0xfff;
-            const double* r = rec + lel * REC;
-            const double* ga = r + ((e >> 12) & 3) * D;
-            const double* gb = r + (e >> 14) * D;
+            const double* ga = rec + (((e >> 12) & 3) * NE + lel) * GS;
+            const double* gb = rec + ((e >> 14) * NE + lel) * GS;
             double a_[D], b_[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) { a_[k] = ga[k]; b_[k] = gb[k]; }
-            const double sq = r[NB * D];
+            const double sq = scal[lel];
 #pragma unroll
             for (int i = 0; i < D; ++i) {
 #pragma unroll
                 for (int k = 0; k < D; ++k) Sm[i * D + k] = fma(a_[i], b_[k], Sm[i * D + k]);
                 t[i] = fma(sq, a_[i], t[i]);
             }
-            V += r[NB * D + 1];
-            W += r[NB * D + 2];
+            V += scal[NE + lel];
+            W += scal[2 * NE + lel];
         }
         const double* mt = smat + slot_mat * TILE_MAT_STRIDE;
         const double mu = mt[0], lam = mt[1], Dc = mt[2], rho = mt[3], beta = mt[5];
@@ -198,13 +206,12 @@ GL_HD void tile_accumulate(const double* rec, const unsigned char* emat, const d
         for (int j = 0; j < L; ++j) {
             const unsigned e = ent[j * 32 + lane];
             const int lel = e & 0xfff;
-            const double* r = rec + lel * REC;
-            const double* ga = r + ((e >> 12) & 3) * D;
-            const double* gb = r + (e >> 14) * D;
+            const double* ga = rec + (((e >> 12) & 3) * NE + lel) * GS;
+            const double* gb = rec + ((e >> 14) * NE + lel) * GS;
             double a_[D], b_[D], gg = 0.0;
 #pragma unroll
             for (int k = 0; k < D; ++k) { a_[k] = ga[k]; b_[k] = gb[k]; gg = fma(a_[k], b_[k], gg); }
-            const double sq = r[NB * D], vol = r[NB * D + 1], vS = r[NB * D + 2];
+            const double sq = scal[lel], vol = scal[NE + lel], vS = scal[2 * NE + lel];
             int m = emat[lel];
             if (m == 255) m = 0;
             const double* mt = smat + m * TILE_MAT_STRIDE;
@@ -258,6 +265,7 @@ GL_HD void tile_finalize(const double (&kf)[TileC<D>::KF], bool diag, double dt,
 // shared-memory carve-up (byte offsets, 16-byte aligned), identical on host and device
 struct TileSmem {
     int lv_cap, el_cap, ent_cap, item_cap, w_cap, n_warps, n_mat;
+    int ne;             // element positions of the record arrays (multiple of 16, > el_cap)
     size_t off_sv, off_rec, off_fw, off_mat, off_ent, off_items, off_emat, off_lcol, total;
 };
 template <int D>
@@ -269,12 +277,13 @@ inline TileSmem tile_smem_layout(int lv_cap, int el_cap, int ent_cap, int item_c
     auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
     size_t o = 0;
     s.off_sv = o;    o = up(o + (size_t)lv_cap * TileC<D>::VS * 8);
-    s.off_rec = o;   o = up(o + (size_t)(el_cap + 1) * TileC<D>::REC * 8);
+    s.ne = (el_cap + TILE_ROWS + 15) & ~15;
+    s.off_rec = o;   o = up(o + (size_t)s.ne * TileC<D>::REC * 8);
     s.off_fw = o;    o = up(o + (size_t)n_warps * 32 * (D + 1) * 8);   // [warp][half][row][NB]
     s.off_mat = o;   o = up(o + (size_t)n_mat * TILE_MAT_STRIDE * 8);
     s.off_ent = o;   o = up(o + (size_t)ent_cap * 2);
     s.off_items = o; o = up(o + (size_t)item_cap * sizeof(TileItem));
-    s.off_emat = o;  o = up(o + (size_t)(el_cap + 1));
+    s.off_emat = o;  o = up(o + (size_t)(el_cap + TILE_ROWS));
     s.off_lcol = o;  o = up(o + (size_t)w_cap * TILE_ROWS * 2);
     s.total = o;
     return s;

@@ -43,42 +43,6 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
         std::sort(elems.begin(), elems.end());
         elems.erase(std::unique(elems.begin(), elems.end()), elems.end());
         const int ne = (int)elems.size();
-        // Element order inside the tile: shared-memory banks repeat every 16 doubles and a record has an odd
-        // stride, so records whose positions differ mod 16 never collide.  Give every element a bucket
-        // (= position mod 16) equal to one of its own rows -- the half-warp lanes that will read it -- choosing the
-        // emptiest candidate so the buckets stay balanced; position = i*16 + bucket.
-        bucket_of.assign(ne, 0);
-        int cnt[TR] = {0};
-        const int target = (ne + TR - 1) / TR + 1;
-        for (int i = 0; i < ne; ++i) {
-            // prefer the smallest own row (translation-consistent on structured meshes: lanes reading "the same"
-            // element of their own neighbourhood then hit distinct banks); overflow goes to the emptiest own row
-            int first = -1, best = -1;
-            for (int a = 0; a < nb; ++a) {
-                int v = cells[(tl_i64)elems[i] * nb + a];
-                if (v >= r0 && v < r0 + nr) {
-                    int m = v - r0;
-                    if (first < 0 || m < first) first = m;
-                    if (best < 0 || cnt[m] < cnt[best]) best = m;
-                }
-            }
-            const int pick = cnt[first] < target ? first : best;
-            bucket_of[i] = pick;
-            cnt[pick]++;
-        }
-        int mxb = 0;
-        for (int m = 0; m < TR; ++m) mxb = std::max(mxb, cnt[m]);
-        pos_of.assign(ne, 0);
-        int n_el;
-        if (TR * mxb <= ne + ne / 4 + TR) {
-            int fill[TR] = {0};
-            for (int i = 0; i < ne; ++i) pos_of[i] = (fill[bucket_of[i]]++) * TR + bucket_of[i];
-            n_el = TR * mxb;
-        } else {                       // very uneven buckets: plain order (bank conflicts, but compact)
-            for (int i = 0; i < ne; ++i) pos_of[i] = i;
-            n_el = ne;
-        }
-        if (n_el + 1 > 4095) { out.ok = false; out.why = "a tile touches more than 4094 elements"; return; }
         // local vertices: own rows first, then the other vertices of the touching elements (ascending)
         lverts.clear();
         for (int i = 0; i < ne; ++i)
@@ -98,17 +62,6 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
         for (int l = 0; l < TR; ++l) out.tv.push_back(l < nr ? r0 + l : -1);
         out.tv.insert(out.tv.end(), lverts.begin(), lverts.end());
         h.n_lv = n_lv;
-        // element records
-        h.e_off = (tl_i64)out.te.size();
-        out.te.resize(out.te.size() + n_el, TILE_NOELEM);
-        for (int i = 0; i < ne; ++i) {
-            unsigned long long r = 0;
-            for (int a = 0; a < nb; ++a)
-                r |= (unsigned long long)local_vertex(cells[(tl_i64)elems[i] * nb + a]) << (12 * a);
-            r |= (unsigned long long)(cell_mat[elems[i]] & 0xff) << 48;
-            out.te[h.e_off + pos_of[i]] = r;
-        }
-        h.n_el = n_el;
         if (n_lv > (1 << TILE_LCOL_BITS)) { out.ok = false; out.why = "a tile references more than 1024 vertices"; return; }
         // contributor lists per slot, and the local column of every slot (padding slots: own row)
         lists.assign((size_t)w * TR, std::vector<uint16_t>());
@@ -121,7 +74,7 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
             for (int j = 0; j < len; ++j) lcol[base + (tl_i64)j * 32 + l] = (uint16_t)local_vertex(col[base + (tl_i64)j * 32 + l]);
             for (tl_i64 t = v2e_ptr[r]; t < v2e_ptr[r + 1]; ++t) {
                 const int e = v2e[t];
-                const int le = pos_of[std::lower_bound(elems.begin(), elems.end(), e) - elems.begin()];
+                const int le = (int)(std::lower_bound(elems.begin(), elems.end(), e) - elems.begin());   // index, not yet a position
                 int a = 0;
                 for (int q = 0; q < nb; ++q) if (cells[(tl_i64)e * nb + q] == r) a = q;
                 for (int b = 0; b < nb; ++b) {
@@ -161,6 +114,76 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
             its.push_back(Item{jA, jB, std::max(cols[jA].L, jB >= 0 ? cols[jB].L : 0), false});
         }
         std::stable_sort(its.begin(), its.end(), [](const Item& a, const Item& b) { return a.L > b.L; });
+        // Element order inside the tile.  Shared-memory banks repeat every 16 doubles and the record arrays have odd
+        // strides, so two elements collide iff their positions agree mod 16.  The 16 lanes of a half-warp read, in
+        // iteration k of an item, 16 (mostly different) elements: walk those access groups and give every element a
+        // bucket (= position mod 16) no other member of its group has yet, preferring the emptiest; position =
+        // rank*16 + bucket.  On structured meshes this is conflict-free; elsewhere it is a greedy best effort.
+        const int cap = (ne + TR - 1) / TR + 5;
+        bucket_of.assign(ne, -1);
+        int cnt[TR] = {0};
+        // preferred bucket: the smallest own row (translates of one element then get distinct buckets); elements of
+        // row 0 that contain the vertex before the tile would belong to "row -1" and prefer the last bucket
+        std::vector<int> pref(ne);
+        for (int i = 0; i < ne; ++i) {
+            int first = TR;
+            bool has_prev = false;
+            for (int a = 0; a < nb; ++a) {
+                int v = cells[(tl_i64)elems[i] * nb + a];
+                if (v >= r0 && v < r0 + nr) first = std::min(first, v - r0);
+                if (v == r0 - 1) has_prev = true;
+            }
+            pref[i] = (first == 0 && has_prev) ? nr - 1 : first;
+        }
+        for (auto& I : its)
+            for (int k = 0; k < I.L; ++k)
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int j = hh == 0 ? I.jA : I.jB;
+                    if (j < 0) continue;
+                    const int q = I.split ? hh * I.L + k : k;
+                    unsigned used = 0;
+                    for (int l = 0; l < TR; ++l) {
+                        auto& li = lists[(size_t)j * TR + l];
+                        if (q < (int)li.size() && bucket_of[li[q] & 0xfff] >= 0) used |= 1u << bucket_of[li[q] & 0xfff];
+                    }
+                    for (int l = 0; l < TR; ++l) {
+                        auto& li = lists[(size_t)j * TR + l];
+                        if (q >= (int)li.size()) continue;
+                        const int e = li[q] & 0xfff;
+                        if (bucket_of[e] >= 0) continue;
+                        int pick = -1, any = 0;
+                        if (!(used >> pref[e] & 1u) && cnt[pref[e]] < cap) pick = pref[e];
+                        else for (int m = 0; m < TR; ++m) {
+                            if (cnt[m] < cnt[any]) any = m;
+                            if (!(used >> m & 1u) && cnt[m] < cap && (pick < 0 || cnt[m] < cnt[pick])) pick = m;
+                        }
+                        if (pick < 0) pick = any;
+                        bucket_of[e] = pick;
+                        cnt[pick]++;
+                        used |= 1u << pick;
+                    }
+                }
+        for (int i = 0; i < ne; ++i) if (bucket_of[i] < 0) { int any = 0; for (int m = 1; m < TR; ++m) if (cnt[m] < cnt[any]) any = m; bucket_of[i] = any; cnt[any]++; }
+        int mxb = 0;
+        for (int m = 0; m < TR; ++m) mxb = std::max(mxb, cnt[m]);
+        pos_of.assign(ne, 0);
+        {
+            int fill[TR] = {0};
+            for (int i = 0; i < ne; ++i) pos_of[i] = (fill[bucket_of[i]]++) * TR + bucket_of[i];
+        }
+        const int n_el = TR * mxb;
+        if (n_el + TR > 4095) { out.ok = false; out.why = "a tile touches more than 4094 elements"; return; }
+        // element records
+        h.e_off = (tl_i64)out.te.size();
+        out.te.resize(out.te.size() + n_el, TILE_NOELEM);
+        for (int i = 0; i < ne; ++i) {
+            unsigned long long r = 0;
+            for (int a = 0; a < nb; ++a)
+                r |= (unsigned long long)local_vertex(cells[(tl_i64)elems[i] * nb + a]) << (12 * a);
+            r |= (unsigned long long)(cell_mat[elems[i]] & 0xff) << 48;
+            out.te[h.e_off + pos_of[i]] = r;
+        }
+        h.n_el = n_el;
         h.item_off = (int)out.items.size();
         h.ent_off = (tl_i64)out.ent.size();
         for (auto& I : its) {
@@ -172,18 +195,34 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
             it.flags = (uint8_t)((cols[I.jA].mixed || (I.jB >= 0 && cols[I.jB].mixed) ? TILE_MIXED : 0) |
                                  (I.split ? TILE_SPLIT : 0) | (I.jB < 0 ? TILE_NULLB : 0));
             it.ent_off = (uint32_t)(out.ent.size() - (size_t)h.ent_off);
-            for (int k = 0; k < I.L; ++k)
+            for (int k = 0; k < I.L; ++k) {
+                uint16_t row_e[32];
+                unsigned used[2] = {0, 0};
                 for (int lane = 0; lane < 32; ++lane) {
                     const int hh = lane >> 4;
                     const int j = hh == 0 ? I.jA : I.jB;
-                    uint16_t e = (uint16_t)n_el;                 // sentinel: zero record, a = b = 0
+                    row_e[lane] = 0xffff;
                     if (j >= 0) {
                         auto& li = lists[(size_t)j * TR + (lane & 15)];
                         const int q = I.split ? hh * I.L + k : k;
-                        if (q < (int)li.size()) e = li[q];
+                        if (q < (int)li.size()) {
+                            row_e[lane] = (uint16_t)((li[q] & 0xf000) | pos_of[li[q] & 0xfff]);
+                            used[hh] |= 1u << (pos_of[li[q] & 0xfff] & 15);
+                        }
                     }
-                    out.ent.push_back(e);
                 }
+                // padding lanes read one of the 16 all-zero records n_el..n_el+15: the one in a bucket no real
+                // element of this half-warp access uses (a = b = 0)
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (row_e[lane] != 0xffff) continue;
+                    const int hh = lane >> 4;
+                    int m = 0;
+                    while (m < TR - 1 && (used[hh] >> m & 1u)) ++m;
+                    used[hh] |= 1u << m;
+                    row_e[lane] = (uint16_t)(n_el + m);
+                }
+                for (int lane = 0; lane < 32; ++lane) out.ent.push_back(row_e[lane]);
+            }
             out.items.push_back(it);
         }
         while (out.ent.size() % 8) out.ent.push_back((uint16_t)n_el);

@@ -13,12 +13,13 @@
 typedef tl_i64 i64;
 
 namespace {
+long long g_bank_wf = 0, g_bank_n = 0, g_hist[9] = {0}; int g_dumped = 0;
 
 template <int D>
 int emulate(const TileMapHost& M, int n_rows, int n_slices, const i64* slice_off, const int* slice_w,
             const double* coords, const double* x, const double* xprev, const double* mat6, int n_mat, double dt,
             const double* fext, double* Kuu, double* Kuc, double* Kcc, double* F) {
-    constexpr int NB = D + 1, REC = TileC<D>::REC, VS = TileC<D>::VS, KF = TileC<D>::KF, TR = TILE_ROWS;
+    constexpr int NB = D + 1, GS = TileC<D>::GS, VS = TileC<D>::VS, KF = TileC<D>::KF, TR = TILE_ROWS;
     const int NW = M.n_warps;
     TileSmem L = tile_smem_layout<D>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.w_cap, NW, n_mat);
     std::vector<unsigned char> smem(L.total);
@@ -43,12 +44,45 @@ int emulate(const TileMapHost& M, int n_rows, int n_slices, const i64* slice_off
             std::memcpy(slcol + j * TR, M.lcol.data() + sbase + (i64)j * 32 + hf * TR, TR * 2);
         std::memcpy(smat, mat6, sizeof(double) * n_mat * TILE_MAT_STRIDE);
         for (int i = 0; i < h.n_lv; ++i) tile_stage_vertex<D>(M.tv[h.v_off + i], coords, x, xprev, sv + i * VS);
-        for (int i = 0; i <= h.n_el; ++i)
-            tile_stage_element<D>(i < h.n_el ? M.te[h.e_off + i] : TILE_NOELEM, sv, rec + i * REC, emat + i);
+        for (int i = 0; i < h.n_el + TR; ++i)
+            tile_stage_element<D>(i < h.n_el ? M.te[h.e_off + i] : TILE_NOELEM, sv, rec, L.ne, i, emat + i);
         std::vector<double> Facc((size_t)NW * 32 * NB, 0.0);
+        static const bool bank_stats = getenv("TILE_EMU_BANKS") != nullptr;
         for (int idx = 0; idx < h.n_items; ++idx) {
             const int warp = idx % NW;
             const TileItem it = sitems[idx];
+            if (bank_stats && getenv("TILE_EMU_DUMP") && T == atoi(getenv("TILE_EMU_DUMP"))) {
+                fprintf(stderr, "tile %d item %d cols %d,%d L %d flags %d\n", T, idx, it.col_j[0], it.col_j[1], it.L, it.flags);
+                for (int j = 0; j < it.L; ++j) {
+                    fprintf(stderr, "  j=%d:", j);
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const unsigned e = sent[it.ent_off + j * 32 + lane];
+                        fprintf(stderr, " %d.%d%d", (int)(e & 0xfff), (int)((e >> 12) & 3), (int)(e >> 14));
+                        if (lane == 15) fprintf(stderr, " |");
+                    }
+                    fprintf(stderr, "\n");
+                }
+            }
+            if (bank_stats) {       // wavefronts of the phase-B LDS.64 loads: per half-warp, max lanes per 8-byte bank
+                for (int j = 0; j < it.L; ++j)
+                    for (int hh = 0; hh < 2; ++hh)
+                        for (int q = 0; q < 2 * D + 3; ++q) {
+                            int cnt[16] = {0}, mx = 0;
+                            std::vector<int> seen;
+                            for (int row = 0; row < 16; ++row) {
+                                const unsigned e = sent[it.ent_off + j * 32 + hh * 16 + row];
+                                const int lel = e & 0xfff, a = (e >> 12) & 3, b = e >> 14;
+                                int w = q < D ? (a * L.ne + lel) * GS + q : q < 2 * D ? (b * L.ne + lel) * GS + (q - D) : NB * L.ne * GS + (q - 2 * D) * L.ne + lel;
+                                bool dup = false;
+                                for (int s2 : seen) if (s2 == w) dup = true;   // same address: broadcast
+                                if (dup) continue;
+                                seen.push_back(w);
+                                mx = std::max(mx, ++cnt[w & 15]);
+                            }
+                            g_bank_wf += mx; g_bank_n += 1; g_hist[std::min(mx, 8)]++;
+                            if (mx == 2 && T >= 4000 && T < 4040 && q == 0 && g_dumped < 24 && getenv("TILE_EMU_WORST")) { g_dumped++; fprintf(stderr, "T=%d item=%d j=%d hh=%d q=%d mx=%d:", T, idx, j, hh, q, mx); for (int row = 0; row < 16; ++row) { unsigned e = sent[it.ent_off + j * 32 + hh * 16 + row]; fprintf(stderr, " %d.%d%d", (int)(e & 0xfff), (int)((e >> 12) & 3), (int)(e >> 14)); } fprintf(stderr, "\n"); }
+                        }
+            }
             double kfs[32][KF];
             int lcs[32];
             for (int lane = 0; lane < 32; ++lane) {
@@ -59,7 +93,7 @@ int emulate(const TileMapHost& M, int n_rows, int n_slices, const i64* slice_off
                 const int lc = lcw & ((1 << TILE_LCOL_BITS) - 1);
                 if (lc >= h.n_lv) return -14;
                 lcs[lane] = lc;
-                tile_accumulate<D>(rec, emat, smat, sent + it.ent_off, it.L, lane, (it.flags & TILE_MIXED) != 0,
+                tile_accumulate<D>(rec, L.ne, emat, smat, sent + it.ent_off, it.L, lane, (it.flags & TILE_MIXED) != 0,
                                    lcw >> TILE_LCOL_BITS, lc == row, dt, kfs[lane]);
             }
             if (it.flags & TILE_SPLIT) {
@@ -159,6 +193,8 @@ extern "C" int tile_emu_assemble(int dim, i64 n_v, i64 n_rows, const double* coo
             } else if (sKcc[s] != 0.0 || sKuu[g * DD + lane] != 0.0) bad++;
         }
     }
+    if (getenv("TILE_EMU_BANKS")) { fprintf(stderr, "wavefront histogram:"); for (int i = 1; i < 9; ++i) fprintf(stderr, " %d:%.3f", i, (double)g_hist[i] / std::max<long long>(1, g_bank_n)); fprintf(stderr, "\n"); }
+    if (getenv("TILE_EMU_BANKS")) fprintf(stderr, "phase-B LDS.64 half-warp wavefronts: %.3f per access (1.0 = conflict-free)\n", (double)g_bank_wf / std::max<long long>(1, g_bank_n));
     if (info) {
         TileSmem L = dim == 2 ? tile_smem_layout<2>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.w_cap, n_warps, n_mat)
                               : tile_smem_layout<3>(M.lv_cap, M.el_cap, M.ent_cap, M.item_cap, M.w_cap, n_warps, n_mat);
