@@ -105,6 +105,7 @@ k_assemble_tile(const TileArgs A, const TileSmem L) {
     for (int idx = warp; idx < h.n_items; idx += NW) {
         const TileItem& it = sitems[idx];      // fields are read from shared memory (hh indexes col_j dynamically)
         const int flags = it.flags;
+        if (flags & TILE_NULLITEM) continue;
         const int cj = it.col_j[hh];
         const int lcw = slcol[cj * TR + row];
         const int lc = lcw & ((1 << TILE_LCOL_BITS) - 1);

@@ -54,7 +54,7 @@ struct TileItem {       // 12 bytes; h = lane >> 4 selects the half-warp
 // MIXED: some lane mixes materials in this column -> per-contributor weights.  SPLIT: both half-warps work on
 // the same (long) column, first / second half of its contributors; the partial sums are combined with a shuffle
 // and half 0 writes.  NULLB: half 1 has no column.
-enum { TILE_MIXED = 1, TILE_SPLIT = 2, TILE_NULLB = 4 };
+enum { TILE_MIXED = 1, TILE_SPLIT = 2, TILE_NULLB = 4, TILE_NULLITEM = 8 /* padding of the warp schedule: skip */ };
 // lcol entry of a slot: local vertex of the column (10 bits) | material of the slot's contributors << 10
 constexpr int TILE_LCOL_BITS = 10;
 constexpr unsigned long long TILE_NOELEM = ~0ULL;
@@ -98,20 +98,35 @@ GL_HD void tile_geometry(const double (&X)[3][2], double (&g)[3][2], double& vol
     g[0][1] = -(g[1][1] + g[2][1]);
     vol = 0.5 * fabs(det);
 }
-GL_HD void tile_geometry(const double (&X)[4][3], double (&g)[4][3], double& vol) {
+// 3D: returns the gradients already scaled by sqrt|K| (what the records store) with one reciprocal square root:
+// grad = cof/det, |K| = |det|/6  =>  sqrt|K| * grad = cof * sign(det) / sqrt(6 |det|),  sqrt|K| = |det| / sqrt(6 |det|).
+GL_HD void tile_geometry_scaled(const double (&X)[4][3], double (&g)[4][3], double& sq, double& vol) {
     double e1[3], e2[3], e3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { e1[k] = X[1][k] - X[0][k]; e2[k] = X[2][k] - X[0][k]; e3[k] = X[3][k] - X[0][k]; }
     double c1[3] = {e2[1] * e3[2] - e2[2] * e3[1], e2[2] * e3[0] - e2[0] * e3[2], e2[0] * e3[1] - e2[1] * e3[0]};
     double c2[3] = {e3[1] * e1[2] - e3[2] * e1[1], e3[2] * e1[0] - e3[0] * e1[2], e3[0] * e1[1] - e3[1] * e1[0]};
     double c3[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-    double det = e1[0] * c1[0] + e1[1] * c1[1] + e1[2] * c1[2], id = 1.0 / det;
+    const double det = e1[0] * c1[0] + e1[1] * c1[1] + e1[2] * c1[2], ad = fabs(det);
+#ifdef __CUDA_ARCH__
+    const double r = rsqrt(6.0 * ad);
+#else
+    const double r = 1.0 / sqrt(6.0 * ad);
+#endif
+    const double s = det < 0.0 ? -r : r;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        g[1][k] = c1[k] * id; g[2][k] = c2[k] * id; g[3][k] = c3[k] * id;
+        g[1][k] = c1[k] * s; g[2][k] = c2[k] * s; g[3][k] = c3[k] * s;
         g[0][k] = -(g[1][k] + g[2][k] + g[3][k]);
     }
-    vol = fabs(det) * (1.0 / 6.0);
+    sq = ad * r;
+    vol = ad * (1.0 / 6.0);
+}
+GL_HD void tile_geometry_scaled(const double (&X)[3][2], double (&g)[3][2], double& sq, double& vol) {
+    tile_geometry(X, g, vol);
+    sq = sqrt(vol);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { g[a][0] *= sq; g[a][1] *= sq; }
 }
 
 // Element records in shared memory, structure of arrays over NE (a multiple of 16) element positions:
@@ -138,13 +153,12 @@ GL_HD void tile_stage_element(unsigned long long rec64, const double* sv, double
         for (int k = 0; k < D; ++k) X[a][k] = p[k];
         S += p[2 * D];
     }
-    double g[NB][D], vol;
-    tile_geometry(X, g, vol);
-    const double sq = sqrt(vol);
+    double g[NB][D], vol, sq;
+    tile_geometry_scaled(X, g, sq, vol);
 #pragma unroll
     for (int a = 0; a < NB; ++a)
 #pragma unroll
-        for (int k = 0; k < D; ++k) rec[(a * NE + i) * GS + k] = sq * g[a][k];
+        for (int k = 0; k < D; ++k) rec[(a * NE + i) * GS + k] = g[a][k];
     sc[0] = sq;
     sc[NE] = vol;
     sc[2 * NE] = vol * S;

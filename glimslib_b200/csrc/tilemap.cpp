@@ -114,6 +114,27 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
             its.push_back(Item{jA, jB, std::max(cols[jA].L, jB >= 0 ? cols[jB].L : 0), false});
         }
         std::stable_sort(its.begin(), its.end(), [](const Item& a, const Item& b) { return a.L > b.L; });
+        {
+            // Warp w processes items w, w + n_warps, ...: balance the warps (longest-processing-time first; an item
+            // costs its iterations plus a fixed share for the conversion and the stores) and lay the list out so
+            // that the stride-n_warps walk realises the assignment; short bins are padded with null items.
+            const int fixed = 4;
+            std::vector<std::vector<Item>> bins(n_warps);
+            std::vector<int> load(n_warps, 0);
+            for (auto& I : its) {
+                int w = 0;
+                for (int q = 1; q < n_warps; ++q) if (load[q] < load[w]) w = q;
+                bins[w].push_back(I);
+                load[w] += I.L + fixed;
+            }
+            size_t depth = 0;
+            for (auto& b : bins) depth = std::max(depth, b.size());
+            its.clear();
+            for (size_t k = 0; k < depth; ++k)
+                for (int w = 0; w < n_warps; ++w)
+                    its.push_back(k < bins[w].size() ? bins[w][k] : Item{-1, -1, 0, false});
+            while (!its.empty() && its.back().jA < 0) its.pop_back();
+        }
         // Element order inside the tile.  Shared-memory banks repeat every 16 doubles and the record arrays have odd
         // strides, so two elements collide iff their positions agree mod 16.  The 16 lanes of a half-warp read, in
         // iteration k of an item, 16 (mostly different) elements: walk those access groups and give every element a
@@ -138,7 +159,7 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
         for (auto& I : its)
             for (int k = 0; k < I.L; ++k)
                 for (int hh = 0; hh < 2; ++hh) {
-                    const int j = hh == 0 ? I.jA : I.jB;
+                    const int j = hh == 0 ? I.jA : I.jB;   // null items have L == 0
                     if (j < 0) continue;
                     const int q = I.split ? hh * I.L + k : k;
                     unsigned used = 0;
@@ -189,6 +210,7 @@ void build_range(int dim, const int* cells, const int* cell_mat, int n_rows, con
         for (auto& I : its) {
             TileItem it;
             std::memset(&it, 0, sizeof it);
+            if (I.jA < 0) { it.flags = TILE_NULLITEM; out.items.push_back(it); continue; }
             it.col_j[0] = (uint16_t)I.jA;
             it.col_j[1] = (uint16_t)(I.jB >= 0 ? I.jB : I.jA);
             it.L = (uint16_t)I.L;

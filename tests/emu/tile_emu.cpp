@@ -51,6 +51,7 @@ int emulate(const TileMapHost& M, int n_rows, int n_slices, const i64* slice_off
         for (int idx = 0; idx < h.n_items; ++idx) {
             const int warp = idx % NW;
             const TileItem it = sitems[idx];
+            if (it.flags & TILE_NULLITEM) continue;
             if (bank_stats && getenv("TILE_EMU_DUMP") && T == atoi(getenv("TILE_EMU_DUMP"))) {
                 fprintf(stderr, "tile %d item %d cols %d,%d L %d flags %d\n", T, idx, it.col_j[0], it.col_j[1], it.L, it.flags);
                 for (int j = 0; j < it.L; ++j) {
