@@ -18,7 +18,7 @@ SYMBOLS = [
     "glims_set_prev", "glims_get_prev", "glims_ndof", "glims_nnzb", "glims_nslots", "glims_state_dev",
     "glims_stream", "glims_step", "glims_assemble", "glims_get_residual", "glims_export_pattern",
     "glims_export_values", "glims_spmv", "glims_time_kernel", "glims_launch_count", "glims_cell_fields",
-    "glims_nccl_unique_id", "glims_comm_init", "glims_set_halo", "glims_tile_info", "glims_tile_config",
+    "glims_nccl_unique_id", "glims_comm_init", "glims_set_halo", "glims_tile_info", "glims_tile_config", "glims_set_p2p", "glims_comm_bench",
 ]
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOT_CONVERGED, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5
@@ -91,6 +91,8 @@ def load():
         "glims_set_halo": (i32, [p, i32, ip, lp, ip, lp]),
         "glims_tile_info": (i32, [p, lp]),
         "glims_tile_config": (i32, [p, i32, i32]),
+        "glims_set_p2p": (i32, [p, i32]),
+        "glims_comm_bench": (i32, [p, i32, i32, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

@@ -1,7 +1,27 @@
-// Multi-GPU plumbing: ghost-vertex halo exchange (grouped ncclSend/ncclRecv) and the Krylov
-// dot-product allreduce.  One context per rank; nothing here runs on a single GPU.
+// Multi-GPU data path: ghost-vertex halo exchange before every operator application and the allreduce of the
+// Krylov scalars.  One context per rank; nothing here runs on a single GPU.
+//
+// Two transports:
+//  * peer memory over NVLink / NVSwitch (default): every rank owns a "window" that all ranks of the box map through
+//    CUDA IPC.  A halo exchange is two kernels per rank -- k_push gathers the owned boundary values and stores them
+//    straight into the neighbours' windows, then publishes a sequence number; k_pull waits for the neighbours'
+//    sequence numbers and copies the received values into the vector's ghost block.  The allreduce is one single-CTA
+//    kernel: all-to-all stores of the partial sums, sequence flags, sum in rank order (bitwise identical on every
+//    rank).  No host involvement, no proxy thread, graph-capturable; latency is a few NVLink round trips instead
+//    of an NCCL kernel + rendezvous per call.
+//  * NCCL grouped send/recv + ncclAllReduce: bootstrap (IPC handle exchange) and fallback (GLIMS_NO_P2P=1, or
+//    peers that cannot map each other's memory).
+//
+// Protocol.  Every rank executes the same sequence of exchanges, so the k-th exchange has the same sequence number
+// everywhere.  Receive buffers are double-buffered by the parity of the sequence number: a neighbour can start
+// exchange k+1 before I have consumed exchange k (other buffer), but it cannot start k+2 before it has consumed my
+// k+1, which I only send after consuming k (stream order) -- so a buffer is never overwritten while it is being read.
+// Waits are bounded (about thirty seconds of SM clock); a timeout raises a device flag that glims_step turns into
+// GLIMS_ERR_NCCL instead of hanging the GPU.
 #include "common.h"
 #include <nccl.h>
+#include <cstdlib>
+#include <cstring>
 
 #define GL_NCCL(call)                                                                  \
     do {                                                                               \
@@ -14,17 +34,270 @@
     } while (0)
 
 namespace {
+
+constexpr int P2P_MAX_RANKS = 8;
+constexpr int RED_MAX = 64;                 // scalars per allreduce (S_GM0 batches use up to 32)
+constexpr long long SPIN_LIMIT = 60000000000LL;  // clock64 ticks (~30 s: ranks may be seconds apart during setup)
+
+// device-visible description of the windows (lives in device memory, one copy per rank)
+struct P2PDev {
+    int n_ranks, rank, n_peers;
+    int peer_rank[P2P_MAX_RANKS];                 // halo neighbours
+    long long send_ptr[P2P_MAX_RANKS + 1];        // my send list is grouped by neighbour
+    long long dst_off[P2P_MAX_RANKS];             // first ghost slot (in vertices) of my values in that neighbour's ghost block
+    long long recv_cnt[P2P_MAX_RANKS];            // ghosts I receive from that neighbour (0: nothing to wait for)
+    unsigned char* win[P2P_MAX_RANKS];            // window base of every rank (own one included), indexed by rank
+    long long halo_bytes;                         // bytes of ONE parity buffer of a window's halo area -- per rank:
+    long long halo_bytes_of[P2P_MAX_RANKS];       //   ... of every rank's window (sizes differ with the ghost count)
+};
+// window layout (byte offsets, identical on every rank except for the size of the halo area)
+constexpr size_t OFF_FLAG_HALO = 0;                                   // u64 [P2P_MAX_RANKS]
+constexpr size_t OFF_FLAG_RED = 64;                                   // u64 [P2P_MAX_RANKS]
+constexpr size_t OFF_SEQ = 128;                                       // u64 seq_halo, seq_red ; u32 done counter ; i32 error
+constexpr size_t OFF_RED = 256;                                       // double [2][P2P_MAX_RANKS][RED_MAX]
+constexpr size_t OFF_HALO = OFF_RED + 2 * P2P_MAX_RANKS * RED_MAX * 8;  // 2 parity buffers of halo_bytes each
+
+struct P2P {
+    bool on = false;
+    unsigned char* win = nullptr;
+    size_t win_bytes = 0;
+    std::vector<void*> opened;        // peer mappings to close
+    P2PDev* dev = nullptr;            // device copy
+    P2PDev host;
+};
+
+__device__ inline unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ inline void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ inline bool spin_until(const unsigned long long* flag, unsigned long long seq, int* err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < seq) {
+        if (clock64() - t0 > SPIN_LIMIT) { *err = 1; return false; }
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// gather my boundary values and store them into the neighbours' windows; the last CTA publishes the sequence number
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_push(const P2PDev* __restrict__ P, const T* __restrict__ x, const int* __restrict__ idx, long long n_send, int bs) {
+    unsigned char* me = P->win[P->rank];
+    unsigned long long* seqp = (unsigned long long*)(me + OFF_SEQ);
+    const unsigned long long seq = *seqp + 1;            // not yet incremented: every CTA reads the same value
+    const int par = (int)(seq & 1);
+    const long long n = n_send * bs;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long v = t / bs;
+        const int k = (int)(t - v * bs);
+        int p = 0;
+        while (p + 1 < P->n_peers && v >= P->send_ptr[p + 1]) ++p;
+        const int r = P->peer_rank[p];
+        T* dst = (T*)(P->win[r] + OFF_HALO + (size_t)par * P->halo_bytes_of[r]);
+        dst[(P->dst_off[p] + (v - P->send_ptr[p])) * bs + k] = x[(long long)idx[v] * bs + k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        unsigned* done = (unsigned*)(me + OFF_SEQ + 16);
+        last = atomicInc(done, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < P->n_peers) {
+            unsigned long long* f = (unsigned long long*)(P->win[P->peer_rank[threadIdx.x]] + OFF_FLAG_HALO) + P->rank;
+            st_release_sys(f, seq);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *seqp = seq;
+    }
+}
+
+// wait for the neighbours' values of the current exchange and copy them into the ghost block of x
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pull(const P2PDev* __restrict__ P, T* __restrict__ x, long long n_owned, long long n_ghost, int bs) {
+    unsigned char* me = P->win[P->rank];
+    const unsigned long long seq = *(const unsigned long long*)(me + OFF_SEQ);     // set by my k_push (stream order)
+    int* err = (int*)(me + OFF_SEQ + 20);
+    if (threadIdx.x < P->n_peers)
+        spin_until((const unsigned long long*)(me + OFF_FLAG_HALO) + P->peer_rank[threadIdx.x], seq, err);
+    __syncthreads();
+    const T* src = (const T*)(me + OFF_HALO + (size_t)(seq & 1) * P->halo_bytes);
+    T* dst = x + n_owned * bs;
+    const long long n = n_ghost * bs;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        dst[t] = __ldcv(&src[t]);
+}
+
+// scal[slot0 .. slot0+n) <- sum over ranks, in rank order on every rank
+__global__ void __launch_bounds__(256)
+k_allreduce(const P2PDev* __restrict__ P, double* __restrict__ scal, int slot0, int n) {
+    unsigned char* me = P->win[P->rank];
+    unsigned long long* seqp = (unsigned long long*)(me + OFF_SEQ + 8);
+    int* err = (int*)(me + OFF_SEQ + 20);
+    const unsigned long long seq = *seqp + 1;
+    const int par = (int)(seq & 1), R = P->n_ranks;
+    for (int t = threadIdx.x; t < R * n; t += blockDim.x) {
+        const int r = t / n, k = t - r * n;
+        double* dst = (double*)(P->win[r] + OFF_RED) + ((size_t)par * P2P_MAX_RANKS + P->rank) * RED_MAX + k;
+        *dst = scal[slot0 + k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < R) st_release_sys((unsigned long long*)(P->win[threadIdx.x] + OFF_FLAG_RED) + P->rank, seq);
+    if (threadIdx.x < R) spin_until((const unsigned long long*)(me + OFF_FLAG_RED) + threadIdx.x, seq, err);
+    __syncthreads();
+    if (threadIdx.x < n) {
+        const double* src = (const double*)(me + OFF_RED) + (size_t)par * P2P_MAX_RANKS * RED_MAX + threadIdx.x;
+        double s = 0.0;
+        for (int r = 0; r < R; ++r) s += __ldcv(&src[(size_t)r * RED_MAX]);
+        scal[slot0 + threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *seqp = seq;
+}
+
 __global__ void k_pack(const double* __restrict__ x, const int* __restrict__ idx, i64 n, int bs, double* buf) {
     i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     if (t >= n * bs) return;
     i64 v = t / bs; int k = (int)(t - v * bs);
     buf[t] = x[(i64)idx[v] * bs + k];
 }
+__global__ void k_pack32(const float* __restrict__ x, const int* __restrict__ idx, i64 n, int bs, float* buf) {
+    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (t >= n * bs) return;
+    i64 v = t / bs; int k = (int)(t - v * bs);
+    buf[t] = x[(i64)idx[v] * bs + k];
+}
+
+inline P2P* p2p_of(glims_ctx* c) {
+    P2P* p = (P2P*)c->halo.p2p;
+    return (p && p->on && c->halo.p2p_enabled) ? p : nullptr;
+}
+
+template <typename T>
+void exchange_p2p(glims_ctx* c, P2P* p, T* xb, int bs) {
+    Halo& h = c->halo;
+    const i64 n_ghost = c->n_v - h.n_owned;
+    if ((size_t)n_ghost * bs * sizeof(T) > (size_t)p->host.halo_bytes) throw GlError(GLIMS_ERR_ARG, "halo exchange: block too wide for the window");
+    const i64 ns = h.n_send * bs;
+    int g = (int)std::min<i64>((ns + 255) / 256, 148 * 4);
+    k_push<T><<<g > 0 ? g : 1, 256, 0, c->stream>>>(p->dev, xb, h.send_idx, h.n_send, bs);
+    const i64 ng = n_ghost * bs;
+    g = (int)std::min<i64>((ng + 255) / 256, 148 * 4);
+    k_pull<T><<<g > 0 ? g : 1, 256, 0, c->stream>>>(p->dev, xb, h.n_owned, n_ghost, bs);
+    c->launches += 2;
+}
+
+// Map every rank's window into this process.  Collective over the NCCL communicator; all ranks agree on the outcome.
+void p2p_setup(glims_ctx* c) {
+    Halo& h = c->halo;
+    if (h.p2p || !h.comm || !h.active) return;
+    if (std::getenv("GLIMS_NO_P2P")) return;
+    const int R = h.n_ranks;
+    if (R > P2P_MAX_RANKS || (int)h.peers.size() > P2P_MAX_RANKS) return;
+    ncclComm_t comm = (ncclComm_t)h.comm;
+    P2P* p = new P2P();
+    h.p2p = p;
+    const i64 n_ghost = c->n_v - h.n_owned;
+    const size_t halo_bytes = (((size_t)n_ghost * 8 * sizeof(double)) + 255) & ~(size_t)255;     // up to 8 doubles per vertex
+    p->win_bytes = OFF_HALO + 2 * halo_bytes;
+    GL_CUDA(cudaMalloc(&p->win, p->win_bytes));
+    GL_CUDA(cudaMemset(p->win, 0, p->win_bytes));
+    // gather: IPC handle (64 B), halo_bytes, and for every rank the ghost offset at which it receives from each rank
+    struct Rec { cudaIpcMemHandle_t h; long long halo_bytes; long long recv_off[P2P_MAX_RANKS]; long long recv_cnt[P2P_MAX_RANKS]; };
+    Rec mine;
+    memset(&mine, 0, sizeof mine);
+    cudaError_t e = cudaIpcGetMemHandle(&mine.h, p->win);
+    int ok = (e == cudaSuccess);
+    if (!ok) cudaGetLastError();
+    mine.halo_bytes = (long long)halo_bytes;
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) { mine.recv_off[r] = -1; mine.recv_cnt[r] = 0; }
+    for (size_t q = 0; q < h.peers.size(); ++q) { mine.recv_off[h.peers[q]] = h.recv_ptr[q]; mine.recv_cnt[h.peers[q]] = h.recv_ptr[q + 1] - h.recv_ptr[q]; }
+    Rec* d_all = nullptr;
+    GL_CUDA(cudaMalloc(&d_all, sizeof(Rec) * R));
+    GL_CUDA(cudaMemcpy(d_all + h.rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+    GL_NCCL(ncclAllGather(d_all + h.rank, d_all, sizeof(Rec), ncclChar, comm, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<Rec> all(R);
+    GL_CUDA(cudaMemcpy(all.data(), d_all, sizeof(Rec) * R, cudaMemcpyDeviceToHost));
+    P2PDev& D = p->host;
+    memset(&D, 0, sizeof D);
+    D.n_ranks = R; D.rank = h.rank; D.n_peers = (int)h.peers.size();
+    D.halo_bytes = (long long)halo_bytes;
+    for (int r = 0; r < R && ok; ++r) {
+        D.halo_bytes_of[r] = all[r].halo_bytes;
+        if (r == h.rank) { D.win[r] = p->win; continue; }
+        void* q = nullptr;
+        e = cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        p->opened.push_back(q);
+        D.win[r] = (unsigned char*)q;
+    }
+    for (size_t q = 0; q < h.peers.size(); ++q) {
+        D.peer_rank[q] = h.peers[q];
+        D.send_ptr[q] = h.send_ptr[q];
+        D.dst_off[q] = all[h.peers[q]].recv_off[h.rank];
+        D.recv_cnt[q] = h.recv_ptr[q + 1] - h.recv_ptr[q];
+        // what I send to q must be what q expects from me
+        if ((h.send_ptr[q + 1] - h.send_ptr[q]) != all[h.peers[q]].recv_cnt[h.rank]) ok = 0;
+        if ((h.send_ptr[q + 1] - h.send_ptr[q]) > 0 && D.dst_off[q] < 0) ok = 0;
+    }
+    D.send_ptr[h.peers.size()] = h.n_send;
+    // all ranks must agree
+    int* d_ok = (int*)d_all;
+    GL_CUDA(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    GL_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    GL_CUDA(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    if (!ok) {
+        if (h.rank == 0) fprintf(stderr, "glims: peer-memory windows unavailable, using NCCL send/recv for the halo exchange\n");
+        return;
+    }
+    GL_CUDA(cudaMalloc(&p->dev, sizeof(P2PDev)));
+    GL_CUDA(cudaMemcpy(p->dev, &D, sizeof(P2PDev), cudaMemcpyHostToDevice));
+    // nobody may push into a window before its owner has zeroed it: one more rendezvous
+    int* d_sync = nullptr;
+    GL_CUDA(cudaMalloc(&d_sync, sizeof(int)));
+    GL_CUDA(cudaMemset(d_sync, 0, sizeof(int)));
+    GL_NCCL(ncclAllReduce(d_sync, d_sync, 1, ncclInt, ncclSum, comm, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_sync);
+    p->on = true;
+}
+
 }  // namespace
+
+void comm_free(glims_ctx* c) {
+    P2P* p = (P2P*)c->halo.p2p;
+    if (!p) return;
+    for (void* q : p->opened) cudaIpcCloseMemHandle(q);
+    if (p->dev) cudaFree(p->dev);
+    if (p->win) cudaFree(p->win);
+    delete p;
+    c->halo.p2p = nullptr;
+}
+
+void comm_check(glims_ctx* c) {
+    P2P* p = (P2P*)c->halo.p2p;
+    if (!p || !p->on) return;
+    int err = 0;
+    GL_CUDA(cudaMemcpy(&err, p->win + OFF_SEQ + 20, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) throw GlError(GLIMS_ERR_NCCL, "peer-memory exchange timed out waiting for a neighbour rank");
+}
 
 void halo_exchange(glims_ctx* c, double* xb, int bs) {
     Halo& h = c->halo;
     if (!h.active || !h.comm) return;
+    if (P2P* p = p2p_of(c)) { exchange_p2p<double>(c, p, xb, bs); return; }
     ncclComm_t comm = (ncclComm_t)h.comm;
     if (h.n_send > 0) {
         i64 n = h.n_send * bs;
@@ -40,18 +313,10 @@ void halo_exchange(glims_ctx* c, double* xb, int bs) {
     GL_NCCL(ncclGroupEnd());
 }
 
-namespace {
-__global__ void k_pack32(const float* __restrict__ x, const int* __restrict__ idx, i64 n, int bs, float* buf) {
-    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    if (t >= n * bs) return;
-    i64 v = t / bs; int k = (int)(t - v * bs);
-    buf[t] = x[(i64)idx[v] * bs + k];
-}
-}  // namespace
-
 void halo_exchange_f32(glims_ctx* c, float* xb, int bs) {
     Halo& h = c->halo;
     if (!h.active || !h.comm) return;
+    if (P2P* p = p2p_of(c)) { exchange_p2p<float>(c, p, xb, bs); return; }
     ncclComm_t comm = (ncclComm_t)h.comm;
     float* sb = (float*)h.send_buf;
     if (h.n_send > 0) {
@@ -71,6 +336,12 @@ void halo_exchange_f32(glims_ctx* c, float* xb, int bs) {
 void allreduce_scalars(glims_ctx* c, int slot0, int n) {
     Halo& h = c->halo;
     if (!h.active || !h.comm) return;
+    if (P2P* p = p2p_of(c)) {
+        if (n > RED_MAX) throw GlError(GLIMS_ERR_ARG, "allreduce: too many scalars");
+        k_allreduce<<<1, 256, 0, c->stream>>>(p->dev, c->scal, slot0, n);
+        c->launches++;
+        return;
+    }
     GL_NCCL(ncclAllReduce(c->scal + slot0, c->scal + slot0, n, ncclDouble, ncclSum, (ncclComm_t)h.comm, c->stream));
 }
 
@@ -91,6 +362,7 @@ int glims_comm_init(glims_ctx* c, int32_t n_ranks, int32_t rank, const void* id1
         ncclComm_t comm;
         GL_NCCL(ncclCommInitRank(&comm, n_ranks, id, rank));
         c->halo.comm = comm; c->halo.n_ranks = n_ranks; c->halo.rank = rank;
+        if (c->halo.send_idx) p2p_setup(c);      // halo plan known (glims_set_halo comes first): map the peer windows
     } catch (const GlError& e) { c->err = e.msg; return e.code; }
     return GLIMS_OK;
 }
@@ -101,6 +373,7 @@ int glims_set_halo(glims_ctx* c, int32_t n_peers, const int32_t* peers, const in
     try {
         GL_CUDA(cudaSetDevice(c->device));
         Halo& h = c->halo;
+        if (h.p2p) throw GlError(GLIMS_ERR_STATE, "set_halo: the halo plan cannot change after glims_comm_init");
         h.peers.assign(peers, peers + n_peers);
         h.send_ptr.assign(send_ptr, send_ptr + n_peers + 1);
         h.recv_ptr.assign(recv_ptr, recv_ptr + n_peers + 1);
@@ -112,6 +385,48 @@ int glims_set_halo(glims_ctx* c, int32_t n_peers, const int32_t* peers, const in
         if (h.n_send > 0) GL_CUDA(cudaMemcpy(h.send_idx, send_idx, sizeof(int) * h.n_send, cudaMemcpyHostToDevice));
         if (h.n_owned + (n_peers ? recv_ptr[n_peers] : 0) != c->n_v)
             throw GlError(GLIMS_ERR_ARG, "set_halo: owned + ghosts != local vertices");
+    } catch (const GlError& e) { c->err = e.msg; return e.code; }
+    return GLIMS_OK;
+}
+
+/* Switch between the peer-memory transport (1, default when the windows could be mapped) and NCCL (0) at run time;
+   must be called with the same value on every rank.  Returns 1 if peer memory is in use afterwards, 0 if not. */
+int glims_set_p2p(glims_ctx* c, int32_t on) {
+    if (!c) return GLIMS_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->halo.p2p_enabled = on != 0;
+    solver_free_graphs(c);          // captured PCG iterations contain the old transport's calls
+    return p2p_of(c) ? 1 : 0;
+}
+
+/* Average device time (microseconds, CUDA events on the context stream) of `reps` back-to-back collectives:
+   kind 0 = halo exchange of the state vector (FP64, dim+1 values per vertex), 1 = FP32 halo exchange with dim values
+   per vertex (the V-cycle's), 2 = allreduce of two scalars. */
+int glims_comm_bench(glims_ctx* c, int32_t kind, int32_t reps, float* us_avg) {
+    if (!c || !us_avg || reps <= 0) return GLIMS_ERR_ARG;
+    try {
+        GL_CUDA(cudaSetDevice(c->device));
+        float* tmp32 = nullptr;
+        if (kind == 1) { GL_CUDA(cudaMalloc(&tmp32, sizeof(float) * c->n_v * c->dim)); GL_CUDA(cudaMemset(tmp32, 0, sizeof(float) * c->n_v * c->dim)); }
+        auto run = [&]() {
+            if (kind == 0) halo_exchange(c, c->dx, c->nb);
+            else if (kind == 1) halo_exchange_f32(c, tmp32, c->dim);
+            else allreduce_scalars(c, S_TMP2, 2);
+        };
+        for (int w = 0; w < 5; ++w) run();
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+        for (int r = 0; r < reps; ++r) run();
+        cudaEventRecord(b, c->stream);
+        GL_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        if (tmp32) cudaFree(tmp32);
+        *us_avg = 1e3f * ms / reps;
+        comm_check(c);
     } catch (const GlError& e) { c->err = e.msg; return e.code; }
     return GLIMS_OK;
 }

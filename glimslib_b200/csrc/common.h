@@ -63,6 +63,8 @@ struct Halo {       // multi-GPU ghost exchange plan (device copies)
     int* send_idx = nullptr;       // device
     double* send_buf = nullptr;    // device, send_ptr.back() * nb doubles (max)
     i64 n_send = 0;
+    void* p2p = nullptr;           // comm.cu: peer-memory windows (NVLink P2P halo exchange / allreduce), null = NCCL path
+    bool p2p_enabled = true;       // runtime switch (glims_set_p2p); GLIMS_NO_P2P=1 disables at setup
 };
 
 struct glims_ctx {
@@ -203,3 +205,6 @@ void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32);   // z = M
 void halo_exchange(glims_ctx* c, double* xb, int bs);        // fill ghost values of a blocked vector
 void halo_exchange_f32(glims_ctx* c, float* xb, int bs);
 void allreduce_scalars(glims_ctx* c, int slot0, int n);      // in-place sum over ranks of c->scal slots
+void comm_free(glims_ctx* c);                                // peer windows (NCCL communicator is left to process exit)
+void comm_check(glims_ctx* c);                               // throws if a peer-memory wait timed out
+void solver_free_graphs(glims_ctx* c);                       // solver.cu: drop captured PCG graphs (transport changed)

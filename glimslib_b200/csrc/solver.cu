@@ -514,6 +514,8 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
 }  // namespace
 
 // ================================================================================================
+void solver_free_graphs(glims_ctx* c) { free_graphs(c); }
+
 #define API_BEGIN if (!c) return GLIMS_ERR_ARG; try { GL_CUDA(cudaSetDevice(c->device));
 #define API_END } catch (const GlError& e) { c->err = e.msg; return e.code; } catch (const std::exception& e) { c->err = e.what(); return GLIMS_ERR_CUDA; } return GLIMS_OK;
 
@@ -577,6 +579,7 @@ int glims_destroy(glims_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->amg) amg_free(c);
     tile_free(c);
+    comm_free(c);
     free_pool(c);
     auto& p = c->pat;
     for (void* q : {(void*)c->coords, (void*)c->cells, (void*)c->cell_mat, (void*)c->mat, (void*)p.slice_off,
@@ -692,6 +695,7 @@ int glims_step(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, glims_
         launch_copy(c, c->x, c->xprev, c->ndof);
     }
     GL_CUDA(cudaStreamSynchronize(c->stream));
+    comm_check(c);
     API_END
 }
 

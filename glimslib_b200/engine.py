@@ -225,6 +225,18 @@ class Engine:
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self._lib.glims_comm_init(self._h, n_ranks, rank, buf), "comm_init")
 
+    def set_p2p(self, on=True):
+        """Halo exchange / allreduce transport: peer-memory windows over NVLink (True) or NCCL (False). Returns what is in use."""
+        rc = self._lib.glims_set_p2p(self._h, int(bool(on)))
+        if rc < 0:
+            self._check(rc, "set_p2p")
+        return bool(rc)
+
+    def comm_bench(self, kind, reps=200):
+        us = C.c_float()
+        self._check(self._lib.glims_comm_bench(self._h, kind, reps, C.byref(us)), "comm_bench")
+        return float(us.value)
+
     def set_halo(self, peers, send_ptr, send_idx, recv_ptr):
         peers = np.ascontiguousarray(peers, dtype=np.int32)
         send_ptr = np.ascontiguousarray(send_ptr, dtype=np.int64)

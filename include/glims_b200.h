@@ -173,7 +173,8 @@ int64_t glims_launch_count(const glims_ctx* c);
 
 /* ---- multi-GPU (one context per rank) ------------------------------------------------------ */
 
-/* Create the rank's NCCL communicator. unique_id: 128 bytes from glims_nccl_unique_id on rank 0. */
+/* Create the rank's NCCL communicator (unique_id: 128 bytes from glims_nccl_unique_id on rank 0) and, when the halo
+   plan is already set (call glims_set_halo first), map every rank's peer-memory window. */
 int glims_nccl_unique_id(void* id128);
 int glims_comm_init(glims_ctx* c, int32_t n_ranks, int32_t rank, const void* id128);
 /* Halo plan: this rank's local vertices are [owned | ghost] (see glims_create).  For each peer p,
@@ -181,6 +182,15 @@ int glims_comm_init(glims_ctx* c, int32_t n_ranks, int32_t rank, const void* id1
    received from p are the contiguous range [recv_ptr[p], recv_ptr[p+1]) of the ghost block. */
 int glims_set_halo(glims_ctx* c, int32_t n_peers, const int32_t* peers, const int64_t* send_ptr,
                    const int32_t* send_idx, const int64_t* recv_ptr);
+
+/* Transport of the halo exchange and of the scalar allreduce: 1 = peer-memory windows over NVLink (CUDA IPC; default
+   whenever every rank can map every other rank's window, csrc/comm.cu), 0 = NCCL send/recv + ncclAllReduce.  Same value on
+   every rank.  Returns 1 if peer memory is in use afterwards, 0 if not, negative on error. */
+int glims_set_p2p(glims_ctx* c, int32_t on);
+/* Average device time (microseconds, CUDA events on the context stream) of `reps` back-to-back collectives on every rank:
+   kind 0 = halo exchange of a state-sized vector (FP64, dim+1 values per vertex), 1 = FP32 halo exchange with dim values
+   per vertex (the one inside the V-cycle), 2 = allreduce of two scalars. */
+int glims_comm_bench(glims_ctx* c, int32_t kind, int32_t reps, float* us_avg);
 
 #ifdef __cplusplus
 }
