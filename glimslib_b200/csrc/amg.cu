@@ -41,6 +41,7 @@ struct Level {
     double *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
     // FP32 copies for the mixed-precision V-cycle (the outer PCG stays FP64)
     float *A32 = nullptr, *dinv32 = nullptr, *x32 = nullptr, *b32 = nullptr, *r32 = nullptr, *d32 = nullptr;
+    float* y32 = nullptr;       // second iterate buffer: the fused smoother steps ping-pong between x32 and y32
 };
 
 }  // namespace
@@ -494,6 +495,121 @@ k_spmv32_split(const i64* __restrict__ slice_off, const int* __restrict__ slice_
     }
 }
 
+// ---- fused smoother steps (FP32 V-cycle) ------------------------------------------------------------
+// First Chebyshev step from a zero guess: x = d = c2 * Dinv * b  (replaces memset + copy + update).
+template <int BS>
+__global__ void k_cheb_first32(const float* __restrict__ dinv, const float* __restrict__ b, float* __restrict__ d,
+                               float* __restrict__ x, int n, float c2) {
+    for (i64 row = blockIdx.x * (i64)TPB + threadIdx.x; row < n; row += (i64)gridDim.x * TPB) {
+        float rv[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) rv[i] = b[row * BS + i];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            float z = 0.f;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) z += dinv[row * BS * BS + i * BS + j] * rv[j];
+            const float dn = c2 * z;
+            d[row * BS + i] = dn;
+            x[row * BS + i] = dn;
+        }
+    }
+}
+
+// One Chebyshev step in one pass over the matrix: r = b - A x (row-local), d = c1 d + c2 Dinv r, xn = x + d.
+// The new iterate goes to a second buffer because other rows still gather the old one.  Thread per block row.
+template <int BS>
+__global__ void __launch_bounds__(TPB)
+k_spmv32_row_cheb(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+                  const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ xn, int n_rows,
+                  const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d, float c1, float c2) {
+    const int n_tiles = (n_rows + TPB - 1) / TPB;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int r = tile * TPB + threadIdx.x;
+        const int S = r >> 5, lane = r & 31;
+        if (S * 32 >= n_rows) continue;
+        float acc[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) acc[i] = 0.f;
+        const i64 base = slice_off[S];
+        const int w = slice_w[S];
+        for (int j = 0; j < w; ++j) {
+            const i64 g = base + (i64)j * 32;
+            const int cidx = __ldg(&col[g + lane]);
+            float xv[BS];
+#pragma unroll
+            for (int b = 0; b < BS; ++b) xv[b] = __ldg(&x[(i64)cidx * BS + b]);
+            const float* Ag = A + g * (BS * BS) + lane;
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+                for (int b = 0; b < BS; ++b) acc[i] += __ldcs(&Ag[(i * BS + b) * 32]) * xv[b];
+        }
+        if (r < n_rows) {
+            float rv[BS];
+#pragma unroll
+            for (int i = 0; i < BS; ++i) rv[i] = rhs[(i64)r * BS + i] - acc[i];
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+                float z = 0.f;
+#pragma unroll
+                for (int j = 0; j < BS; ++j) z += dinv[(i64)r * BS * BS + i * BS + j] * rv[j];
+                const float dn = c2 * z + (c1 != 0.f ? c1 * d[(i64)r * BS + i] : 0.f);
+                d[(i64)r * BS + i] = dn;
+                xn[(i64)r * BS + i] = x[(i64)r * BS + i] + dn;
+            }
+        }
+    }
+}
+
+// Same step for the coarse levels: CTA per slice, warp i computes component i of the slice's 32 block rows; the residual
+// block of a row is exchanged through shared memory so that every thread can apply its row of Dinv.
+template <int BS>
+__global__ void __launch_bounds__(32 * BS)
+k_spmv32_split_cheb(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+                    const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ xn, int n_rows,
+                    int n_slices, const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d,
+                    float c1, float c2) {
+    __shared__ float rs[BS][32];
+    const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
+    for (int S = blockIdx.x; S < n_slices; S += gridDim.x) {
+        const int r = S * 32 + lane;
+        const i64 base = slice_off[S];
+        const int w = slice_w[S];
+        float acc0 = 0.f, acc1 = 0.f;
+        int j = 0;
+        for (; j + 1 < w; j += 2) {
+            const i64 g0 = base + (i64)j * 32, g1 = g0 + 32;
+            const int c0 = __ldg(&col[g0 + lane]), c1i = __ldg(&col[g1 + lane]);
+            const float* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+            const float* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < BS; ++b) {
+                acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+                acc1 += __ldcs(&A1[b * 32]) * __ldg(&x[(i64)c1i * BS + b]);
+            }
+        }
+        if (j < w) {
+            const i64 g0 = base + (i64)j * 32;
+            const int c0 = __ldg(&col[g0 + lane]);
+            const float* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+        }
+        rs[i][lane] = r < n_rows ? rhs[(i64)r * BS + i] - (acc0 + acc1) : 0.f;
+        __syncthreads();
+        if (r < n_rows) {
+            float z = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < BS; ++jj) z += dinv[(i64)r * BS * BS + i * BS + jj] * rs[jj][lane];
+            const float dn = c2 * z + (c1 != 0.f ? c1 * d[(i64)r * BS + i] : 0.f);
+            d[(i64)r * BS + i] = dn;
+            xn[(i64)r * BS + i] = x[(i64)r * BS + i] + dn;
+        }
+        __syncthreads();
+    }
+}
+
 template <int BS>
 __global__ void k_cheb_update32(const float* __restrict__ dinv, const float* __restrict__ r, float* __restrict__ d,
                                 float* __restrict__ x, int n, float c1, float c2) {
@@ -593,33 +709,38 @@ void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) 
     c->launches++;
 }
 
-void smooth32(glims_ctx* c, Amg* amg, Level& l, const float* b, float* x, bool zero_guess, bool fine) {
-    const double lmax = l.lmax, lmin = amg->cheb_ratio * lmax;
-    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
-    double rho = 1.0 / sigma;
-    for (int k = 0; k < amg->cheb_degree; ++k) {
-        if (k == 0 && zero_guess) {
-            GL_CUDA(cudaMemcpyAsync(l.r32, b, sizeof(float) * (i64)l.n * l.bs, cudaMemcpyDeviceToDevice, c->stream));
-        } else {
-            if (fine) halo_exchange_f32(c, x, l.bs);
-            spmv32(c, l, x, l.r32, b);
-        }
-        double c1, c2;
-        if (k == 0) { c1 = 0.0; c2 = 1.0 / theta; }
-        else {
-            double rho_new = 1.0 / (2.0 * sigma - rho);
-            c1 = rho_new * rho;
-            c2 = 2.0 * rho_new / delta;
-            rho = rho_new;
-        }
-        int g = sgrid(l.n);
-        if (l.bs == 2) k_cheb_update32<2><<<g, TPB, 0, c->stream>>>(l.dinv32, l.r32, l.d32, x, l.n, (float)c1, (float)c2);
-        else if (l.bs == 3) k_cheb_update32<3><<<g, TPB, 0, c->stream>>>(l.dinv32, l.r32, l.d32, x, l.n, (float)c1, (float)c2);
-        else k_cheb_update32<6><<<g, TPB, 0, c->stream>>>(l.dinv32, l.r32, l.d32, x, l.n, (float)c1, (float)c2);
-        c->launches++;
+// one fused Chebyshev step: xn = x + d_new  with  d_new = c1 d + c2 Dinv (b - A x)
+void cheb_step32(glims_ctx* c, Level& l, const float* b, const float* x, float* xn, float c1, float c2) {
+    auto& p = l.pat;
+    if (l.owns_A) {      // coarse levels: split kernel, like spmv32
+        int g = p.n_slices < 148 * 16 ? p.n_slices : 148 * 16;
+        if (g < 1) g = 1;
+        if (l.bs == 6) k_spmv32_split_cheb<6><<<g, 192, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, p.n_slices, b, l.dinv32, l.d32, c1, c2);
+        else k_spmv32_split_cheb<3><<<g, 96, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, p.n_slices, b, l.dinv32, l.d32, c1, c2);
+    } else {
+        int g = sgrid(p.n_rows);
+        if (l.bs == 2) k_spmv32_row_cheb<2><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2);
+        else k_spmv32_row_cheb<3><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2);
     }
+    c->launches++;
 }
 
+struct ChebCoef {                 // Chebyshev recurrence for the interval [ratio * lmax, lmax] of Dinv A
+    double theta, delta, sigma, rho;
+    ChebCoef(double lmax, double ratio) {
+        const double lmin = ratio * lmax;
+        theta = 0.5 * (lmax + lmin); delta = 0.5 * (lmax - lmin); sigma = theta / delta; rho = 1.0 / sigma;
+    }
+    void step(int k, double& c1, double& c2) {
+        if (k == 0) { c1 = 0.0; c2 = 1.0 / theta; return; }
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        c1 = rho_new * rho; c2 = 2.0 * rho_new / delta; rho = rho_new;
+    }
+};
+
+// V-cycle in FP32 with fused smoother steps.  The iterate ping-pongs between l.y32 and x; with `degree` pre- and
+// post-smoothing steps there are 2*degree-1 fused steps after the first (zero-guess) one, an odd number, so starting
+// in l.y32 leaves the result in x.
 void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
     Level& l = amg->L[li];
     const int D = amg->dim;
@@ -631,18 +752,42 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
     }
     Level& lc = amg->L[li + 1];
     const bool l0 = (li == 0);
-    GL_CUDA(cudaMemsetAsync(x, 0, sizeof(float) * (i64)l.n * l.bs, c->stream));
-    smooth32(c, amg, l, b, x, true, l0);
-    if (l0) halo_exchange_f32(c, x, l.bs);
-    spmv32(c, l, x, l.r32, b);
+    float *cur = l.y32, *oth = x;
+    double c1, c2;
+    {   // pre-smoothing from a zero guess
+        ChebCoef cc(l.lmax, amg->cheb_ratio);
+        cc.step(0, c1, c2);
+        const int g = sgrid(l.n);
+        if (l.bs == 2) k_cheb_first32<2><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, l.n, (float)c2);
+        else if (l.bs == 3) k_cheb_first32<3><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, l.n, (float)c2);
+        else k_cheb_first32<6><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, l.n, (float)c2);
+        c->launches++;
+        for (int k = 1; k < amg->cheb_degree; ++k) {
+            cc.step(k, c1, c2);
+            if (l0) halo_exchange_f32(c, cur, l.bs);
+            cheb_step32(c, l, b, cur, oth, (float)c1, (float)c2);
+            std::swap(cur, oth);
+        }
+    }
+    if (l0) halo_exchange_f32(c, cur, l.bs);
+    spmv32(c, l, cur, l.r32, b);
     if (D == 2) k_restrict32<2><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
     else k_restrict32<3><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
     c->launches++;
     vcycle32(c, amg, li + 1, lc.b32, lc.x32);
-    if (D == 2) k_prolong_add32<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, x);
-    else k_prolong_add32<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, x);
+    if (D == 2) k_prolong_add32<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
+    else k_prolong_add32<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
     c->launches++;
-    smooth32(c, amg, l, b, x, false, l0);
+    {   // post-smoothing
+        ChebCoef cc(l.lmax, amg->cheb_ratio);
+        for (int k = 0; k < amg->cheb_degree; ++k) {
+            cc.step(k, c1, c2);
+            if (l0) halo_exchange_f32(c, cur, l.bs);
+            cheb_step32(c, l, b, cur, oth, (float)c1, (float)c2);
+            std::swap(cur, oth);
+        }
+    }
+    if (cur != x) GL_CUDA(cudaMemcpyAsync(x, cur, sizeof(float) * (i64)l.n * l.bs, cudaMemcpyDeviceToDevice, c->stream));
 }
 
 void build_fp32(glims_ctx* c, Amg* amg) {
@@ -652,7 +797,7 @@ void build_fp32(glims_ctx* c, Amg* amg) {
         GL_CUDA(cudaMalloc(&l.dinv32, sizeof(float) * std::max<i64>(nd, 1)));
         k_to_float<<<sgrid(na), TPB, 0, c->stream>>>(l.A, l.A32, na);
         k_to_float<<<sgrid(nd), TPB, 0, c->stream>>>(l.dinv, l.dinv32, nd);
-        for (float** v : {&l.x32, &l.b32, &l.r32, &l.d32}) {
+        for (float** v : {&l.x32, &l.b32, &l.r32, &l.d32, &l.y32}) {
             GL_CUDA(cudaMalloc(v, sizeof(float) * std::max<i64>(nv, 1)));
             GL_CUDA(cudaMemsetAsync(*v, 0, sizeof(float) * std::max<i64>(nv, 1), c->stream));
         }
@@ -668,7 +813,7 @@ void free_level(Level& l) {
     if (l.owns_A && l.A) cudaFree(l.A);
     for (void* q : {(void*)l.dinv, (void*)l.agg, (void*)l.rvec, (void*)l.free_mask, (void*)l.mem_ptr, (void*)l.mem_idx,
                     (void*)l.X, (void*)l.x, (void*)l.b, (void*)l.r, (void*)l.d, (void*)l.A32, (void*)l.dinv32,
-                    (void*)l.x32, (void*)l.b32, (void*)l.r32, (void*)l.d32})
+                    (void*)l.x32, (void*)l.b32, (void*)l.r32, (void*)l.d32, (void*)l.y32})
         if (q) cudaFree(q);
 }
 

@@ -3,9 +3,9 @@
 //
 // Two transports:
 //  * peer memory over NVLink / NVSwitch (default): every rank owns a "window" that all ranks of the box map through
-//    CUDA IPC.  A halo exchange is two kernels per rank -- k_push gathers the owned boundary values and stores them
-//    straight into the neighbours' windows, then publishes a sequence number; k_pull waits for the neighbours'
-//    sequence numbers and copies the received values into the vector's ghost block.  The allreduce is one single-CTA
+//    CUDA IPC.  A halo exchange is one kernel per rank (k_halo): gather the owned boundary values, store them
+//    straight into the neighbours' windows, publish a sequence number, wait for the neighbours' sequence numbers
+//    and copy the received values into the vector's ghost block.  The allreduce is one single-CTA
 //    kernel: all-to-all stores of the partial sums, sequence flags, sum in rank order (bitwise identical on every
 //    rank).  No host involvement, no proxy thread, graph-capturable; latency is a few NVLink round trips instead
 //    of an NCCL kernel + rendezvous per call.
@@ -53,7 +53,7 @@ struct P2PDev {
 // window layout (byte offsets, identical on every rank except for the size of the halo area)
 constexpr size_t OFF_FLAG_HALO = 0;                                   // u64 [P2P_MAX_RANKS]
 constexpr size_t OFF_FLAG_RED = 64;                                   // u64 [P2P_MAX_RANKS]
-constexpr size_t OFF_SEQ = 128;                                       // u64 seq_halo, seq_red ; u32 done counter ; i32 error
+constexpr size_t OFF_SEQ = 128;                                       // u64 seq_halo, seq_red ; u32 pushed ; i32 error ; u32 left
 constexpr size_t OFF_RED = 256;                                       // double [2][P2P_MAX_RANKS][RED_MAX]
 constexpr size_t OFF_HALO = OFF_RED + 2 * P2P_MAX_RANKS * RED_MAX * 8;  // 2 parity buffers of halo_bytes each
 
@@ -83,14 +83,20 @@ __device__ inline bool spin_until(const unsigned long long* flag, unsigned long 
     return true;
 }
 
-// gather my boundary values and store them into the neighbours' windows; the last CTA publishes the sequence number
+// One kernel per halo exchange.  Every CTA (1) gathers its share of my boundary values and stores them straight into
+// the neighbours' windows, (2) the CTA that finishes last publishes the sequence number to the neighbours, (3) every CTA
+// waits for the neighbours' sequence numbers and copies its share of the received values into the ghost block of x.
+// No CTA waits for another CTA of this grid (only for the neighbours, whose publication does not depend on mine), so the
+// kernel cannot deadlock even when the grid is larger than what is resident at once.
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_push(const P2PDev* __restrict__ P, const T* __restrict__ x, const int* __restrict__ idx, long long n_send, int bs) {
+k_halo(const P2PDev* __restrict__ P, T* __restrict__ x, const int* __restrict__ idx, long long n_send, int bs,
+       long long n_owned, long long n_ghost) {
     unsigned char* me = P->win[P->rank];
     unsigned long long* seqp = (unsigned long long*)(me + OFF_SEQ);
-    const unsigned long long seq = *seqp + 1;            // not yet incremented: every CTA reads the same value
-    const int par = (int)(seq & 1);
+    int* err = (int*)(me + OFF_SEQ + 20);
+    const unsigned long long seq = *seqp + 1;            // incremented by the last CTA on its way out; all CTAs of this
+    const int par = (int)(seq & 1);                      // grid read the same value (see the exit protocol below)
     const long long n = n_send * bs;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const long long v = t / bs;
@@ -104,37 +110,26 @@ k_push(const P2PDev* __restrict__ P, const T* __restrict__ x, const int* __restr
     __threadfence_system();
     __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) {
-        unsigned* done = (unsigned*)(me + OFF_SEQ + 16);
-        last = atomicInc(done, gridDim.x - 1) == gridDim.x - 1;
-    }
+    unsigned* done = (unsigned*)(me + OFF_SEQ + 16);
+    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
     __syncthreads();
     if (last) {
         __threadfence_system();
-        if (threadIdx.x < P->n_peers) {
-            unsigned long long* f = (unsigned long long*)(P->win[P->peer_rank[threadIdx.x]] + OFF_FLAG_HALO) + P->rank;
-            st_release_sys(f, seq);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) *seqp = seq;
+        if (threadIdx.x < P->n_peers)
+            st_release_sys((unsigned long long*)(P->win[P->peer_rank[threadIdx.x]] + OFF_FLAG_HALO) + P->rank, seq);
     }
-}
-
-// wait for the neighbours' values of the current exchange and copy them into the ghost block of x
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_pull(const P2PDev* __restrict__ P, T* __restrict__ x, long long n_owned, long long n_ghost, int bs) {
-    unsigned char* me = P->win[P->rank];
-    const unsigned long long seq = *(const unsigned long long*)(me + OFF_SEQ);     // set by my k_push (stream order)
-    int* err = (int*)(me + OFF_SEQ + 20);
     if (threadIdx.x < P->n_peers)
         spin_until((const unsigned long long*)(me + OFF_FLAG_HALO) + P->peer_rank[threadIdx.x], seq, err);
     __syncthreads();
-    const T* src = (const T*)(me + OFF_HALO + (size_t)(seq & 1) * P->halo_bytes);
+    const T* src = (const T*)(me + OFF_HALO + (size_t)par * P->halo_bytes);
     T* dst = x + n_owned * bs;
-    const long long n = n_ghost * bs;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    const long long ng = n_ghost * bs;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ng; t += (long long)gridDim.x * blockDim.x)
         dst[t] = __ldcv(&src[t]);
+    // exit protocol: the sequence number advances only after every CTA has read it
+    __syncthreads();
+    unsigned* gone = (unsigned*)(me + OFF_SEQ + 24);     // separate counter: a fast CTA may leave before a slow one has pushed
+    if (threadIdx.x == 0 && atomicAdd(gone, 1u) == gridDim.x - 1) { *done = 0; *gone = 0; __threadfence(); *seqp = seq; }
 }
 
 // scal[slot0 .. slot0+n) <- sum over ranks, in rank order on every rank
@@ -187,13 +182,10 @@ void exchange_p2p(glims_ctx* c, P2P* p, T* xb, int bs) {
     Halo& h = c->halo;
     const i64 n_ghost = c->n_v - h.n_owned;
     if ((size_t)n_ghost * bs * sizeof(T) > (size_t)p->host.halo_bytes) throw GlError(GLIMS_ERR_ARG, "halo exchange: block too wide for the window");
-    const i64 ns = h.n_send * bs;
-    int g = (int)std::min<i64>((ns + 255) / 256, 148 * 4);
-    k_push<T><<<g > 0 ? g : 1, 256, 0, c->stream>>>(p->dev, xb, h.send_idx, h.n_send, bs);
-    const i64 ng = n_ghost * bs;
-    g = (int)std::min<i64>((ng + 255) / 256, 148 * 4);
-    k_pull<T><<<g > 0 ? g : 1, 256, 0, c->stream>>>(p->dev, xb, h.n_owned, n_ghost, bs);
-    c->launches += 2;
+    const i64 n = std::max(h.n_send, n_ghost) * bs;
+    int g = (int)std::min<i64>((n + 255) / 256, 148 * 2);
+    k_halo<T><<<g > 0 ? g : 1, 256, 0, c->stream>>>(p->dev, xb, h.send_idx, h.n_send, bs, h.n_owned, n_ghost);
+    c->launches++;
 }
 
 // Map every rank's window into this process.  Collective over the NCCL communicator; all ranks agree on the outcome.
