@@ -8,8 +8,12 @@
 // Fully constrained (Dirichlet) vertices and ghost vertices are left out of the coarse space, so on a
 // partitioned mesh the preconditioner is rank-local (block-Jacobi over sub-domains) with no communication.
 #include "common.h"
+#include <cuda_fp16.h>
 #include <thrust/device_ptr.h>
 #include <thrust/device_vector.h>
+#include <thrust/transform_reduce.h>
+#include <thrust/functional.h>
+#include <thrust/execution_policy.h>
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -41,6 +45,8 @@ struct Level {
     double *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
     // FP32 copies for the mixed-precision V-cycle (the outer PCG stays FP64)
     float *A32 = nullptr, *dinv32 = nullptr, *x32 = nullptr, *b32 = nullptr, *r32 = nullptr, *d32 = nullptr;
+    __half* A16 = nullptr;      // fine level only (optional): matrix values in FP16, scaled by a power of two
+    float a16_unscale = 1.f;    // multiply row sums by this to undo the scaling
     float* y32 = nullptr;       // second iterate buffer: the fused smoother steps ping-pong between x32 and y32
 };
 
@@ -418,16 +424,24 @@ void vcycle(glims_ctx* c, Amg* amg, int li, const double* b, double* x) {
 __global__ void k_to_float(const double* __restrict__ a, float* __restrict__ b, i64 n) {
     for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) b[i] = (float)a[i];
 }
+__global__ void k_to_half(const double* __restrict__ a, __half* __restrict__ b, i64 n, double scale) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) b[i] = __double2half(a[i] * scale);
+}
+struct AbsD { __host__ __device__ double operator()(double v) const { return v < 0 ? -v : v; } };
 __global__ void k_to_double(const float* __restrict__ a, double* __restrict__ b, i64 n) {
     for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) b[i] = (double)a[i];
 }
 
-// thread per block row (fine level, BS = 2|3): y = A x  or  y = rhs - A x
-template <int BS, bool RESID>
+__device__ inline float ld_mat(const float* p) { return __ldcs(p); }
+__device__ inline float ld_mat(const __half* p) { return __half2float(__ldcs(p)); }
+
+// thread per block row (fine level, BS = 2|3): y = A x  or  y = rhs - A x.  MT = float, or __half with the values
+// scaled by a power of two (unscale restores the row sums; FP32 accumulation either way)
+template <int BS, bool RESID, typename MT>
 __global__ void __launch_bounds__(TPB)
 k_spmv32_row(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
-             const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ y, int n_rows,
-             const float* __restrict__ rhs) {
+             const MT* __restrict__ A, const float* __restrict__ x, float* __restrict__ y, int n_rows,
+             const float* __restrict__ rhs, float unscale) {
     const int n_tiles = (n_rows + TPB - 1) / TPB;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int r = tile * TPB + threadIdx.x;
@@ -444,15 +458,15 @@ k_spmv32_row(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
             float xv[BS];
 #pragma unroll
             for (int b = 0; b < BS; ++b) xv[b] = __ldg(&x[(i64)cidx * BS + b]);
-            const float* Ag = A + g * (BS * BS) + lane;
+            const MT* Ag = A + g * (BS * BS) + lane;
 #pragma unroll
             for (int i = 0; i < BS; ++i)
 #pragma unroll
-                for (int b = 0; b < BS; ++b) acc[i] += __ldcs(&Ag[(i * BS + b) * 32]) * xv[b];
+                for (int b = 0; b < BS; ++b) acc[i] += ld_mat(&Ag[(i * BS + b) * 32]) * xv[b];
         }
         if (r < n_rows) {
 #pragma unroll
-            for (int i = 0; i < BS; ++i) y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - acc[i] : acc[i];
+            for (int i = 0; i < BS; ++i) y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - unscale * acc[i] : unscale * acc[i];
         }
     }
 }
@@ -518,11 +532,12 @@ __global__ void k_cheb_first32(const float* __restrict__ dinv, const float* __re
 
 // One Chebyshev step in one pass over the matrix: r = b - A x (row-local), d = c1 d + c2 Dinv r, xn = x + d.
 // The new iterate goes to a second buffer because other rows still gather the old one.  Thread per block row.
-template <int BS>
+template <int BS, typename MT>
 __global__ void __launch_bounds__(TPB)
 k_spmv32_row_cheb(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
-                  const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ xn, int n_rows,
-                  const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d, float c1, float c2) {
+                  const MT* __restrict__ A, const float* __restrict__ x, float* __restrict__ xn, int n_rows,
+                  const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d, float c1, float c2,
+                  float unscale) {
     const int n_tiles = (n_rows + TPB - 1) / TPB;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int r = tile * TPB + threadIdx.x;
@@ -539,16 +554,16 @@ k_spmv32_row_cheb(const i64* __restrict__ slice_off, const int* __restrict__ sli
             float xv[BS];
 #pragma unroll
             for (int b = 0; b < BS; ++b) xv[b] = __ldg(&x[(i64)cidx * BS + b]);
-            const float* Ag = A + g * (BS * BS) + lane;
+            const MT* Ag = A + g * (BS * BS) + lane;
 #pragma unroll
             for (int i = 0; i < BS; ++i)
 #pragma unroll
-                for (int b = 0; b < BS; ++b) acc[i] += __ldcs(&Ag[(i * BS + b) * 32]) * xv[b];
+                for (int b = 0; b < BS; ++b) acc[i] += ld_mat(&Ag[(i * BS + b) * 32]) * xv[b];
         }
         if (r < n_rows) {
             float rv[BS];
 #pragma unroll
-            for (int i = 0; i < BS; ++i) rv[i] = rhs[(i64)r * BS + i] - acc[i];
+            for (int i = 0; i < BS; ++i) rv[i] = rhs[(i64)r * BS + i] - unscale * acc[i];
 #pragma unroll
             for (int i = 0; i < BS; ++i) {
                 float z = 0.f;
@@ -698,12 +713,21 @@ void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) 
         }
     } else {
         int g = sgrid(p.n_rows);
-        if (l.bs == 2) {
-            if (rhs) k_spmv32_row<2, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, rhs);
-            else k_spmv32_row<2, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, nullptr);
+        if (l.A16) {
+            const float us = l.a16_unscale;
+            if (l.bs == 2) {
+                if (rhs) k_spmv32_row<2, true, __half><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A16, x, y, p.n_rows, rhs, us);
+                else k_spmv32_row<2, false, __half><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A16, x, y, p.n_rows, nullptr, us);
+            } else {
+                if (rhs) k_spmv32_row<3, true, __half><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A16, x, y, p.n_rows, rhs, us);
+                else k_spmv32_row<3, false, __half><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A16, x, y, p.n_rows, nullptr, us);
+            }
+        } else if (l.bs == 2) {
+            if (rhs) k_spmv32_row<2, true, float><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, rhs, 1.f);
+            else k_spmv32_row<2, false, float><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, nullptr, 1.f);
         } else {
-            if (rhs) k_spmv32_row<3, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, rhs);
-            else k_spmv32_row<3, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, nullptr);
+            if (rhs) k_spmv32_row<3, true, float><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, rhs, 1.f);
+            else k_spmv32_row<3, false, float><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, nullptr, 1.f);
         }
     }
     c->launches++;
@@ -719,8 +743,11 @@ void cheb_step32(glims_ctx* c, Level& l, const float* b, const float* x, float* 
         else k_spmv32_split_cheb<3><<<g, 96, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, p.n_slices, b, l.dinv32, l.d32, c1, c2);
     } else {
         int g = sgrid(p.n_rows);
-        if (l.bs == 2) k_spmv32_row_cheb<2><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2);
-        else k_spmv32_row_cheb<3><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2);
+        if (l.A16) {
+            if (l.bs == 2) k_spmv32_row_cheb<2, __half><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A16, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2, l.a16_unscale);
+            else k_spmv32_row_cheb<3, __half><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A16, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2, l.a16_unscale);
+        } else if (l.bs == 2) k_spmv32_row_cheb<2, float><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2, 1.f);
+        else k_spmv32_row_cheb<3, float><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2, 1.f);
     }
     c->launches++;
 }
@@ -791,11 +818,28 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
 }
 
 void build_fp32(glims_ctx* c, Amg* amg) {
+    // Fine level in FP16 (GLIMS_AMG_FP16=0 keeps FP32): the smoother streams this matrix four times per V-cycle and is
+    // bandwidth bound; the V-cycle is only a preconditioner (a fixed SPD operator as long as the rounded matrix is
+    // symmetric, which it is: K(r,c) and K(c,r)^T round identically), the outer PCG stays FP64.
+    const char* e16 = std::getenv("GLIMS_AMG_FP16");
+    const bool want16 = !(e16 && atoi(e16) == 0);
     for (auto& l : amg->L) {
         i64 na = l.pat.n_slots * l.bs * l.bs, nd = (i64)l.n * l.bs * l.bs, nv = std::max<i64>(l.n_cols, l.n) * l.bs;
-        GL_CUDA(cudaMalloc(&l.A32, sizeof(float) * std::max<i64>(na, 1)));
+        const bool fine16 = want16 && !l.owns_A && &l == &amg->L[0] && amg->L.size() > 1 && na > 0;
+        if (fine16) {
+            thrust::device_ptr<const double> ap(l.A);
+            const double amax = thrust::transform_reduce(thrust::cuda::par.on(c->stream), ap, ap + na, AbsD(), 0.0, thrust::maximum<double>());
+            int ex = 0;
+            if (amax > 0) { std::frexp(amax, &ex); }
+            const double scale = std::ldexp(1.0, 14 - ex);       // largest magnitude lands in [2^13, 2^14)
+            GL_CUDA(cudaMalloc(&l.A16, sizeof(__half) * na));
+            k_to_half<<<sgrid(na), TPB, 0, c->stream>>>(l.A, l.A16, na, scale);
+            l.a16_unscale = (float)(1.0 / scale);
+        } else {
+            GL_CUDA(cudaMalloc(&l.A32, sizeof(float) * std::max<i64>(na, 1)));
+            k_to_float<<<sgrid(na), TPB, 0, c->stream>>>(l.A, l.A32, na);
+        }
         GL_CUDA(cudaMalloc(&l.dinv32, sizeof(float) * std::max<i64>(nd, 1)));
-        k_to_float<<<sgrid(na), TPB, 0, c->stream>>>(l.A, l.A32, na);
         k_to_float<<<sgrid(nd), TPB, 0, c->stream>>>(l.dinv, l.dinv32, nd);
         for (float** v : {&l.x32, &l.b32, &l.r32, &l.d32, &l.y32}) {
             GL_CUDA(cudaMalloc(v, sizeof(float) * std::max<i64>(nv, 1)));
@@ -813,7 +857,7 @@ void free_level(Level& l) {
     if (l.owns_A && l.A) cudaFree(l.A);
     for (void* q : {(void*)l.dinv, (void*)l.agg, (void*)l.rvec, (void*)l.free_mask, (void*)l.mem_ptr, (void*)l.mem_idx,
                     (void*)l.X, (void*)l.x, (void*)l.b, (void*)l.r, (void*)l.d, (void*)l.A32, (void*)l.dinv32,
-                    (void*)l.x32, (void*)l.b32, (void*)l.r32, (void*)l.d32, (void*)l.y32})
+                    (void*)l.x32, (void*)l.b32, (void*)l.r32, (void*)l.d32, (void*)l.y32, (void*)l.A16})
         if (q) cudaFree(q);
 }
 

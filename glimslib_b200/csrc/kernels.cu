@@ -929,6 +929,14 @@ __global__ void k_pcg_shift(double* scal, double* ring) {
     ring[64] = (double)(it + 1);
     scal[S_RZ] = scal[S_RZNEW];
 }
+// condition of the PCG iteration's IF node: run the body while the last r.r (ring) is above tol^2 (ring[66]);
+// NaN compares false and stops the loop.  ring[64] counts the iterations that really ran.
+__global__ void k_pcg_cond(cudaGraphConditionalHandle handle, const double* __restrict__ ring) {
+    const int it = (int)ring[64];
+    unsigned go = 1u;
+    if (it > 0) go = ring[(it - 1) & 63] > ring[66] ? 1u : 0u;
+    cudaGraphSetConditional(handle, go);
+}
 __global__ void k_flush(double* buf, i64 n) {
     for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) buf[i] = (double)i;
 }
@@ -1194,6 +1202,10 @@ void launch_extrapolate_c(glims_ctx* c, double* x, const double* xold) {
 }
 void launch_pcg_shift(glims_ctx* c, double* ring) {
     k_pcg_shift<<<1, 1, 0, c->stream>>>(c->scal, ring);
+    LAUNCHED(c);
+}
+void launch_pcg_cond(glims_ctx* c, unsigned long long handle, const double* ring) {
+    k_pcg_cond<<<1, 1, 0, c->stream>>>((cudaGraphConditionalHandle)handle, ring);
     LAUNCHED(c);
 }
 void flush_l2(glims_ctx* c) {

@@ -10,6 +10,7 @@
 
 void launch_split_norms(glims_ctx* c, const double* F, int s0);
 void launch_pcg_shift(glims_ctx* c, double* ring);
+void launch_pcg_cond(glims_ctx* c, unsigned long long handle, const double* ring);
 void launch_extrapolate_c(glims_ctx* c, double* x, const double* xold);
 void launch_cell_fields(glims_ctx* c, double* out, double* vol);
 void launch_cell_to_vertex(glims_ctx* c, int nf, const double* q, const double* vol, double* num, double* den);
@@ -22,7 +23,7 @@ struct GraphKey {
         return std::tie(which, pc, amg, x, r, bs) < std::tie(o.which, o.pc, o.amg, o.x, o.r, o.bs);
     }
 };
-struct PcgGraph { cudaGraphExec_t exec = nullptr; i64 launches = 0; bool failed = false; };
+struct PcgGraph { cudaGraphExec_t exec = nullptr; i64 launches = 0; bool failed = false; bool conditional = false; };
 
 // Everything the host drivers keep per context (no process-global state: contexts may live on different threads)
 struct SolverState {
@@ -99,6 +100,65 @@ void apply_pc(glims_ctx* c, int which, int pc, const double* r, double* z, int s
     launch_block_jacobi(c, c->dinv_mono, c->nb, r, z, nrows(c), s_rz);
 }
 
+// One PCG iteration as an executable graph.  Preferred form: [k_pcg_cond] -> IF(body = captured iteration), so that a
+// launch after convergence is a no-op; if the conditional node cannot be built (driver, or a library call that refuses
+// to be captured into a body graph) the iteration is captured as a plain graph, as before.
+template <typename F>
+bool build_pcg_graph(glims_ctx* c, PcgGraph* G, double* ring, F&& iteration) {
+    const bool want_cond = std::getenv("GLIMS_NO_COND_GRAPH") == nullptr;
+    if (want_cond) {
+        cudaGraph_t g = nullptr, tmp = nullptr;
+        bool ok = cudaGraphCreate(&g, 0) == cudaSuccess;
+        cudaGraphConditionalHandle h = 0;
+        ok = ok && cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+        if (ok) {
+            ok = cudaStreamBeginCaptureToGraph(c->stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                launch_pcg_cond(c, (unsigned long long)h, ring);
+                ok = cudaStreamEndCapture(c->stream, &tmp) == cudaSuccess;
+            }
+        }
+        cudaGraphNode_t knode = nullptr, cnode = nullptr;
+        size_t nn = 1;
+        ok = ok && cudaGraphGetNodes(g, &knode, &nn) == cudaSuccess && nn == 1;
+        cudaGraph_t body = nullptr;
+        if (ok) {
+            cudaGraphNodeParams cp = {};
+            cp.type = cudaGraphNodeTypeConditional;
+            cp.conditional.handle = h;
+            cp.conditional.type = cudaGraphCondTypeIf;
+            cp.conditional.size = 1;
+            ok = cudaGraphAddNode(&cnode, g, &knode, 1, &cp) == cudaSuccess;
+            if (ok) body = cp.conditional.phGraph_out[0];
+        }
+        if (ok) {
+            ok = cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                try { iteration(); } catch (const GlError&) { ok = false; }
+                if (cudaStreamEndCapture(c->stream, &tmp) != cudaSuccess) ok = false;
+            }
+        }
+        if (ok && cudaGraphInstantiate(&G->exec, g, 0) != cudaSuccess) { ok = false; G->exec = nullptr; }
+        if (g) cudaGraphDestroy(g);
+        if (ok) { G->conditional = true; c->launches += 1; return true; }
+        cudaGetLastError();
+        // make sure the stream is not left in capture mode
+        cudaStreamCaptureStatus st;
+        if (cudaStreamIsCapturing(c->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) cudaStreamEndCapture(c->stream, &tmp);
+        cudaGetLastError();
+    }
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+        try { iteration(); } catch (const GlError&) { ok = false; }
+        if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess || !graph) ok = false;
+    }
+    if (ok && cudaGraphInstantiate(&G->exec, graph, 0) != cudaSuccess) { ok = false; G->exec = nullptr; }
+    if (graph) cudaGraphDestroy(graph);
+    G->conditional = false;
+    return ok;
+}
+
 // PCG on block `which` (1: K_uu, 2: K_cc), zero initial guess. Returns iterations, or -1 if not converged.
 constexpr int REC_KEEP = 10;   // solutions whose span survives a compression
 
@@ -169,46 +229,60 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
         allreduce_scalars(c, S_RR, 2);               // S_RR and S_RZNEW are adjacent: one message
         launch_cg_update_p(c, p, z, n, S_RZNEW, S_RZ);
         launch_pcg_shift(c, ring);
-        GL_CUDA(cudaMemcpyAsync(c->h_ring, ring, sizeof(double) * 64, cudaMemcpyDeviceToHost, c->stream));
+        GL_CUDA(cudaMemcpyAsync(c->h_ring, ring, sizeof(double) * 65, cudaMemcpyDeviceToHost, c->stream));
     };
+    // Convergence test on the device: ring[66] holds tol^2; the captured iteration is the body of a conditional (IF)
+    // graph node whose condition is "the last r.r is still above tol^2" (k_pcg_cond).  The host can therefore queue
+    // several iterations ahead -- no GPU idling on the host's convergence check -- and iterations queued past
+    // convergence cost one tiny kernel instead of a full iteration.
+    const double tol2 = tol * tol;
+    GL_CUDA(cudaMemcpyAsync(ring + 66, &tol2, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     GraphKey key{which, pc, (void*)c->amg, (void*)x, (void*)r, bs};
     PcgGraph* G = c->use_graphs ? &state(c).graphs[key] : nullptr;
-    cudaEvent_t ev[2];
-    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
-    int result = -1;
-    for (int it = 1; it <= maxit + 1; ++it) {
-        if (it <= maxit) {
+    constexpr int NEV = 8;
+    cudaEvent_t ev[NEV];
+    for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    const int lookahead = (G && !G->failed) ? (which == 1 ? 2 : 4) : 1;      // launches in flight beyond the one inspected
+    int result = -1, launched = 0, checked = 0, seen = 0, cond_launched = 0, plain_its = 0;
+    bool bad = false;
+    while (result < 0 && !bad && checked < maxit) {
+        while (launched < maxit && launched < checked + 1 + ((G && G->exec && G->conditional) ? lookahead : 1)) {
+            const int it = launched + 1;
             if (G && G->exec) {
                 GL_CUDA(cudaGraphLaunch(G->exec, c->stream));
-                c->launches += G->launches;
+                if (G->conditional) { c->launches += 1; cond_launched++; }      // body kernels are counted once we know they ran
+                else c->launches += G->launches;
             } else if (G && !G->failed && it >= 2) {
                 // second iteration of the first solve with this configuration: all buffers exist -> capture
                 i64 l0 = c->launches;
-                cudaGraph_t graph = nullptr;
-                bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
-                if (ok) {
-                    try { iteration(); } catch (const GlError&) { ok = false; }
-                    if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess || !graph) ok = false;
-                }
-                if (ok && cudaGraphInstantiate(&G->exec, graph, 0) != cudaSuccess) { ok = false; G->exec = nullptr; }
-                if (graph) cudaGraphDestroy(graph);
+                bool ok = build_pcg_graph(c, G, ring, iteration);
                 G->launches = c->launches - l0;
                 c->launches = l0;
-                if (!ok) { G->failed = true; cudaGetLastError(); iteration(); }
-                else { GL_CUDA(cudaGraphLaunch(G->exec, c->stream)); c->launches += G->launches; }
-            } else iteration();
-            GL_CUDA(cudaEventRecord(ev[it & 1], c->stream));
+                if (!ok) { G->failed = true; cudaGetLastError(); iteration(); plain_its++; }
+                else {
+                    GL_CUDA(cudaGraphLaunch(G->exec, c->stream));
+                    if (G->conditional) { c->launches += 1; cond_launched++; } else c->launches += G->launches;
+                }
+            } else { iteration(); plain_its++; }
+            GL_CUDA(cudaEventRecord(ev[launched % NEV], c->stream));
+            launched++;
         }
-        if (it >= 2) {   // inspect the previous iteration while this one is already queued
-            GL_CUDA(cudaEventSynchronize(ev[(it - 1) & 1]));
-            double rn = std::sqrt(c->h_ring[(it - 2) & 63]);
-            if (res_out) *res_out = rn;
-            if (!(rn == rn)) { result = -1; break; }
-            if (rn <= tol) { result = std::min(it, maxit); break; }
+        GL_CUDA(cudaEventSynchronize(ev[checked % NEV]));
+        checked++;
+        // iterations that really ran so far (skipped bodies do not advance the device counter)
+        const int n_done = std::min((int)c->h_ring[64], launched);
+        for (int k = seen + 1; k <= n_done && result < 0; ++k) {
+            const double rr = c->h_ring[(k - 1) & 63];
+            if (res_out) *res_out = std::sqrt(rr);
+            if (!(rr == rr)) { bad = true; break; }
+            if (rr <= tol2) result = k;
         }
+        seen = n_done;
+        if (n_done < checked && result < 0) bad = true;      // device stopped but the host test did not fire: NaN
     }
-    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (G && G->conditional && cond_launched > 0)      // kernels of the conditional bodies that really executed
+        c->launches += (i64)std::max(0, std::min(seen - plain_its, cond_launched)) * (G->launches - 1);
     if (recycle) {
         if (result >= 0) {
             // A w = r0 - r_final for the correction w = x (PCG started from zero on r0)
