@@ -152,6 +152,9 @@ def algorithmic_bytes(d, n_v, n_c, nnzb):
         "spmv_kcc": 12 * nnzb + 16 * n_v,
         "assembly_full": n_c * (4 * nb + 8 * d * nb + 4) + 8 * (d * d + d + 1) * nnzb + 3 * 8 * nb * n_v,
         "residual": n_c * (4 * nb + 8 * d * nb + 4) + 3 * 8 * nb * n_v,
+        # fused Chebyshev smoother step of the V-cycle's fine level: FP16 d x d blocks + int32 column per block;
+        # per vertex FP32 x (gathered, counted once), rhs, Dinv (d x d), d (read + write), own x, new x
+        "smoother_step": (2 * d * d + 4) * nnzb + 4 * (d + d + d * d + 2 * d + d + d) * n_v,
     }
 
 
@@ -262,23 +265,36 @@ def main():
         peak, peak_src = peaks()
         n_v, n_c, nnzb = eng.n_owned, eng.n_cells, eng.nnzb
         ab = algorithmic_bytes(d, n_v, n_c, nnzb)
-        for name, kid, variant, key in (("spmv_kuu", 2, 0, "spmv_kuu"), ("spmv_mono", 1, 0, "spmv_mono"),
+        for name, kid, variant, key in (("smoother_step_fp16", 6, 0, "smoother_step"),
+                                        ("spmv_kuu", 2, 0, "spmv_kuu"), ("spmv_mono", 1, 0, "spmv_mono"),
                                         ("spmv_kcc", 3, 0, "spmv_kcc"),
                                         ("assembly_full_tile", 0, 3, "assembly_full"),
                                         ("assembly_full_slice", 0, 2, "assembly_full"),
                                         ("assembly_full_gather", 0, 1, "assembly_full"),
                                         ("assembly_full_atomic", 0, 0, "assembly_full"),
                                         ("residual", 4, 0, "residual"), ("residual_kcc", 5, 0, "residual")):
+            if kid == 6 and args.pc != "amg":
+                continue
             ms = eng.time_kernel(kid, variant, reps=10, flush_l2=True)
             gbs = ab[key] / ms / 1e6
             kernels[name] = {"ms": ms, "algorithmic_bytes": ab[key], "achieved_gbs": gbs, "frac": gbs / peak}
-        k = kernels["spmv_kuu"]
-        roof = {"bound": "hbm", "kernel": "k_spmv_block<3,3> (K_uu SELL-32 SpMV inside PCG)", "achieved": k["achieved_gbs"],
-                "peak": peak, "unit": "GB/s", "frac": k["frac"],
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
-                # kernel on this workload (profiles/r01_ncu_summary.md); only valid for the default mesh on one GPU
-                "traffic": 2.070e9 if (args.n == 148 and world == 1) else None,
-                "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, r01)", "peak_source": peak_src}
+        one_gpu_default = (args.n == 148 and world == 1)
+        if "smoother_step_fp16" in kernels:
+            # dominant kernel of the step: 3 launches per PCG iteration, 25 % of the kernel time in the ncu launch list
+            # of this command (profiles/r01_launch_summary_final.csv); next are the coarse-level smoother steps (22 %)
+            # and the FP64 K_uu SpMV of PCG (18 %), both listed under "kernels"
+            k = kernels["smoother_step_fp16"]
+            roof = {"bound": "hbm", "kernel": "k_spmv32_row_cheb<3,__half> (fused Chebyshev smoother step, fine level of the V-cycle)",
+                    "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": k["frac"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this kernel on this
+                    # workload (profiles/r01_ncu_summary.md); only valid for the default mesh on one GPU
+                    "traffic": 788.5e6 if one_gpu_default else None,
+                    "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, r01 final build)", "peak_source": peak_src}
+        else:
+            k = kernels["spmv_kuu"]
+            roof = {"bound": "hbm", "kernel": "k_spmv_block<3,3> (K_uu SELL-32 SpMV inside PCG)", "achieved": k["achieved_gbs"],
+                    "peak": peak, "unit": "GB/s", "frac": k["frac"], "traffic": 2.070e9 if one_gpu_default else None,
+                    "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, r01)", "peak_source": peak_src}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -291,7 +307,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "n_tets": int(w["mesh"].num_cells()),
                        "n_vertices": int(w["mesh"].num_vertices()), "n_dofs": int(w["mesh"].num_vertices() * 4),
-                       "nnz_blocks": int(eng.nnzb), "dt": w["dt"], "solver": "block-triangular Newton-PCG, pc=%s (aggregation AMG, FP32-storage V-cycle) + successive-RHS projection" % args.pc,
+                       "nnz_blocks": int(eng.nnzb), "dt": w["dt"], "solver": "block-triangular Newton-PCG, pc=%s (aggregation AMG; V-cycle in FP32 with an FP16 fine-level matrix, fused smoother steps) + successive-RHS projection; PCG iterations replayed as conditional CUDA graphs" % args.pc,
                        "tolerances": "SNES rtol 1e-9 atol 1e-10 (monolithic |F|), KSP rtol 1e-10",
                        "timing": "inputs larger than L2 (matrix 1.9 GB, vectors 42-56 MB); wall clock between "
                                  "device syncs, max over ranks",

@@ -472,11 +472,11 @@ k_spmv32_row(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
 }
 
 // CTA per slice, warp per block-row component (coarse levels, BS = 3|6)
-template <int BS, bool RESID>
+template <int BS, bool RESID, typename MT>
 __global__ void __launch_bounds__(32 * BS)
 k_spmv32_split(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
-               const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ y, int n_rows,
-               int n_slices, const float* __restrict__ rhs) {
+               const MT* __restrict__ A, const float* __restrict__ x, float* __restrict__ y, int n_rows,
+               int n_slices, const float* __restrict__ rhs, float unscale) {
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
     for (int S = blockIdx.x; S < n_slices; S += gridDim.x) {
         const int r = S * 32 + lane;
@@ -487,23 +487,23 @@ k_spmv32_split(const i64* __restrict__ slice_off, const int* __restrict__ slice_
         for (; j + 1 < w; j += 2) {
             const i64 g0 = base + (i64)j * 32, g1 = g0 + 32;
             const int c0 = __ldg(&col[g0 + lane]), c1 = __ldg(&col[g1 + lane]);
-            const float* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
-            const float* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
+            const MT* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+            const MT* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
 #pragma unroll
             for (int b = 0; b < BS; ++b) {
-                acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
-                acc1 += __ldcs(&A1[b * 32]) * __ldg(&x[(i64)c1 * BS + b]);
+                acc0 += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+                acc1 += ld_mat(&A1[b * 32]) * __ldg(&x[(i64)c1 * BS + b]);
             }
         }
         if (j < w) {
             const i64 g0 = base + (i64)j * 32;
             const int c0 = __ldg(&col[g0 + lane]);
-            const float* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+            const MT* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
 #pragma unroll
-            for (int b = 0; b < BS; ++b) acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+            for (int b = 0; b < BS; ++b) acc0 += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
         }
         if (r < n_rows) {
-            const float v = acc0 + acc1;
+            const float v = unscale * (acc0 + acc1);
             y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - v : v;
         }
     }
@@ -579,12 +579,12 @@ k_spmv32_row_cheb(const i64* __restrict__ slice_off, const int* __restrict__ sli
 
 // Same step for the coarse levels: CTA per slice, warp i computes component i of the slice's 32 block rows; the residual
 // block of a row is exchanged through shared memory so that every thread can apply its row of Dinv.
-template <int BS>
+template <int BS, typename MT>
 __global__ void __launch_bounds__(32 * BS)
 k_spmv32_split_cheb(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
-                    const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ xn, int n_rows,
+                    const MT* __restrict__ A, const float* __restrict__ x, float* __restrict__ xn, int n_rows,
                     int n_slices, const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d,
-                    float c1, float c2) {
+                    float c1, float c2, float unscale) {
     __shared__ float rs[BS][32];
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
     for (int S = blockIdx.x; S < n_slices; S += gridDim.x) {
@@ -596,22 +596,22 @@ k_spmv32_split_cheb(const i64* __restrict__ slice_off, const int* __restrict__ s
         for (; j + 1 < w; j += 2) {
             const i64 g0 = base + (i64)j * 32, g1 = g0 + 32;
             const int c0 = __ldg(&col[g0 + lane]), c1i = __ldg(&col[g1 + lane]);
-            const float* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
-            const float* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
+            const MT* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+            const MT* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
 #pragma unroll
             for (int b = 0; b < BS; ++b) {
-                acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
-                acc1 += __ldcs(&A1[b * 32]) * __ldg(&x[(i64)c1i * BS + b]);
+                acc0 += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+                acc1 += ld_mat(&A1[b * 32]) * __ldg(&x[(i64)c1i * BS + b]);
             }
         }
         if (j < w) {
             const i64 g0 = base + (i64)j * 32;
             const int c0 = __ldg(&col[g0 + lane]);
-            const float* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
+            const MT* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
 #pragma unroll
-            for (int b = 0; b < BS; ++b) acc0 += __ldcs(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+            for (int b = 0; b < BS; ++b) acc0 += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
         }
-        rs[i][lane] = r < n_rows ? rhs[(i64)r * BS + i] - (acc0 + acc1) : 0.f;
+        rs[i][lane] = r < n_rows ? rhs[(i64)r * BS + i] - unscale * (acc0 + acc1) : 0.f;
         __syncthreads();
         if (r < n_rows) {
             float z = 0.f;
@@ -704,13 +704,15 @@ void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) 
     if (l.owns_A) {      // coarse levels (6x6 blocks in 3D, 3x3 in 2D): few rows, use the split kernel
         int g = p.n_slices < 148 * 16 ? p.n_slices : 148 * 16;
         if (g < 1) g = 1;
-        if (l.bs == 6) {
-            if (rhs) k_spmv32_split<6, true><<<g, 192, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, p.n_slices, rhs);
-            else k_spmv32_split<6, false><<<g, 192, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, p.n_slices, nullptr);
+#define SPLIT_GO(BS, RES, MT, AP, US) k_spmv32_split<BS, RES, MT><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, y, p.n_rows, p.n_slices, rhs, US)
+        if (l.A16) {
+            if (l.bs == 6) { if (rhs) SPLIT_GO(6, true, __half, l.A16, l.a16_unscale); else SPLIT_GO(6, false, __half, l.A16, l.a16_unscale); }
+            else { if (rhs) SPLIT_GO(3, true, __half, l.A16, l.a16_unscale); else SPLIT_GO(3, false, __half, l.A16, l.a16_unscale); }
         } else {
-            if (rhs) k_spmv32_split<3, true><<<g, 96, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, p.n_slices, rhs);
-            else k_spmv32_split<3, false><<<g, 96, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, y, p.n_rows, p.n_slices, nullptr);
+            if (l.bs == 6) { if (rhs) SPLIT_GO(6, true, float, l.A32, 1.f); else SPLIT_GO(6, false, float, l.A32, 1.f); }
+            else { if (rhs) SPLIT_GO(3, true, float, l.A32, 1.f); else SPLIT_GO(3, false, float, l.A32, 1.f); }
         }
+#undef SPLIT_GO
     } else {
         int g = sgrid(p.n_rows);
         if (l.A16) {
@@ -739,8 +741,10 @@ void cheb_step32(glims_ctx* c, Level& l, const float* b, const float* x, float* 
     if (l.owns_A) {      // coarse levels: split kernel, like spmv32
         int g = p.n_slices < 148 * 16 ? p.n_slices : 148 * 16;
         if (g < 1) g = 1;
-        if (l.bs == 6) k_spmv32_split_cheb<6><<<g, 192, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, p.n_slices, b, l.dinv32, l.d32, c1, c2);
-        else k_spmv32_split_cheb<3><<<g, 96, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A32, x, xn, p.n_rows, p.n_slices, b, l.dinv32, l.d32, c1, c2);
+#define SPLITC_GO(BS, MT, AP, US) k_spmv32_split_cheb<BS, MT><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, xn, p.n_rows, p.n_slices, b, l.dinv32, l.d32, c1, c2, US)
+        if (l.A16) { if (l.bs == 6) SPLITC_GO(6, __half, l.A16, l.a16_unscale); else SPLITC_GO(3, __half, l.A16, l.a16_unscale); }
+        else { if (l.bs == 6) SPLITC_GO(6, float, l.A32, 1.f); else SPLITC_GO(3, float, l.A32, 1.f); }
+#undef SPLITC_GO
     } else {
         int g = sgrid(p.n_rows);
         if (l.A16) {
@@ -825,7 +829,8 @@ void build_fp32(glims_ctx* c, Amg* amg) {
     const bool want16 = !(e16 && atoi(e16) == 0);
     for (auto& l : amg->L) {
         i64 na = l.pat.n_slots * l.bs * l.bs, nd = (i64)l.n * l.bs * l.bs, nv = std::max<i64>(l.n_cols, l.n) * l.bs;
-        const bool fine16 = want16 && !l.owns_A && &l == &amg->L[0] && amg->L.size() > 1 && na > 0;
+        // default: the fine level only (the coarse-level kernels are latency bound: measured no gain); GLIMS_AMG_FP16=2: every smoothed level
+        const bool fine16 = want16 && &l != &amg->L.back() && na > 0 && (&l == &amg->L[0] || (e16 && atoi(e16) >= 2));
         if (fine16) {
             thrust::device_ptr<const double> ap(l.A);
             const double amax = thrust::transform_reduce(thrust::cuda::par.on(c->stream), ap, ap + na, AbsD(), 0.0, thrust::maximum<double>());
@@ -1000,6 +1005,15 @@ void amg_setup(glims_ctx* c) {
     for (size_t li = 0; li + 1 < amg->L.size(); ++li) estimate_lmax(c, amg->L[li]);
     GL_CUDA(cudaStreamSynchronize(c->stream));
     build_fp32(c, amg);
+}
+
+// one fused smoother step on the fine level with the hierarchy's own buffers (roofline bench, glims_time_kernel 6)
+bool amg_time_fine_step(glims_ctx* c) {
+    Amg* amg = c->amg;
+    if (!amg || amg->L.size() < 2 || !amg->L[0].dinv32) return false;
+    Level& l = amg->L[0];
+    cheb_step32(c, l, l.b32, l.x32, l.y32, 0.3f, 0.5f);
+    return true;
 }
 
 void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32) {

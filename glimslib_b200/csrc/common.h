@@ -199,7 +199,8 @@ void flush_l2(glims_ctx* c);
 // ---------------- amg.cu
 void amg_setup(glims_ctx* c);
 void amg_free(glims_ctx* c);
-void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32);   // z = M^-1 r on K_uu ([n_v][dim] vectors)
+void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32);
+bool amg_time_fine_step(glims_ctx* c);     // false: no FP32 hierarchy yet   // z = M^-1 r on K_uu ([n_v][dim] vectors)
 
 // ---------------- comm.cu
 void halo_exchange(glims_ctx* c, double* xb, int bs);        // fill ghost values of a blocked vector

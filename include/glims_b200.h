@@ -150,7 +150,8 @@ int glims_spmv(glims_ctx* c, int32_t which, const double* x, double* y);
 /* Average device time (ms, CUDA events on the context stream) of `reps` back-to-back launches of
    one kernel on resident data: kernel 0 = full assembly (residual+Jacobian, `variant` = GLIMS_ASMK_*),
    1 = monolithic SpMV, 2 = K_uu SpMV, 3 = K_cc SpMV, 4 = residual only, 5 = residual + K_cc (the per-Newton-iteration
-   pass of the block-triangular solver). flush_l2 != 0 writes a
+   pass of the block-triangular solver), 6 = one fused Chebyshev smoother step of the V-cycle's fine level (FP16 matrix,
+   FP32 vectors; needs a step with GLIMS_PC_AMG first). flush_l2 != 0 writes a
    >L2-sized buffer between launches (outside the timed events). */
 int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t reps, int32_t flush_l2,
                       float* ms_avg);
