@@ -23,7 +23,7 @@ struct GraphKey {
         return std::tie(which, pc, amg, x, r, bs) < std::tie(o.which, o.pc, o.amg, o.x, o.r, o.bs);
     }
 };
-struct PcgGraph { cudaGraphExec_t exec = nullptr; i64 launches = 0; bool failed = false; bool conditional = false; };
+struct PcgGraph { cudaGraphExec_t exec = nullptr; i64 launches = 0; bool failed = false; bool conditional = false; int its = 1; };
 
 // Everything the host drivers keep per context (no process-global state: contexts may live on different threads)
 struct SolverState {
@@ -104,7 +104,7 @@ void apply_pc(glims_ctx* c, int which, int pc, const double* r, double* z, int s
 // launch after convergence is a no-op; if the conditional node cannot be built (driver, or a library call that refuses
 // to be captured into a body graph) the iteration is captured as a plain graph, as before.
 template <typename F>
-bool build_pcg_graph(glims_ctx* c, PcgGraph* G, double* ring, F&& iteration) {
+bool build_pcg_graph(glims_ctx* c, PcgGraph* G, double* ring, F&& iteration, int unroll) {
     const bool want_cond = std::getenv("GLIMS_NO_COND_GRAPH") == nullptr;
     if (want_cond) {
         cudaGraph_t g = nullptr, tmp = nullptr;
@@ -134,13 +134,13 @@ bool build_pcg_graph(glims_ctx* c, PcgGraph* G, double* ring, F&& iteration) {
         if (ok) {
             ok = cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
             if (ok) {
-                try { iteration(); } catch (const GlError&) { ok = false; }
+                try { for (int u = 0; u < unroll; ++u) iteration(); } catch (const GlError&) { ok = false; }
                 if (cudaStreamEndCapture(c->stream, &tmp) != cudaSuccess) ok = false;
             }
         }
         if (ok && cudaGraphInstantiate(&G->exec, g, 0) != cudaSuccess) { ok = false; G->exec = nullptr; }
         if (g) cudaGraphDestroy(g);
-        if (ok) { G->conditional = true; c->launches += 1; return true; }
+        if (ok) { G->conditional = true; G->its = unroll; c->launches += 1; return true; }
         cudaGetLastError();
         // make sure the stream is not left in capture mode
         cudaStreamCaptureStatus st;
@@ -156,6 +156,7 @@ bool build_pcg_graph(glims_ctx* c, PcgGraph* G, double* ring, F&& iteration) {
     if (ok && cudaGraphInstantiate(&G->exec, graph, 0) != cudaSuccess) { ok = false; G->exec = nullptr; }
     if (graph) cudaGraphDestroy(graph);
     G->conditional = false;
+    G->its = 1;
     return ok;
 }
 
@@ -242,35 +243,44 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
     constexpr int NEV = 8;
     cudaEvent_t ev[NEV];
     for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    const int lookahead = (G && !G->failed) ? (which == 1 ? 2 : 4) : 1;      // launches in flight beyond the one inspected
-    int result = -1, launched = 0, checked = 0, seen = 0, cond_launched = 0, plain_its = 0;
+    // cheap iterations (K_cc: one scalar SpMV) are captured several to a body, so that the per-launch cost of the
+    // conditional node is amortised; at most unroll-1 extra iterations run after convergence (harmless: alpha and
+    // beta guard against 0/0)
+    static const int unroll_c = std::getenv("GLIMS_PCG_UNROLL") ? std::max(1, atoi(std::getenv("GLIMS_PCG_UNROLL"))) : 4;
+    const int unroll = which == 2 ? unroll_c : 1;
+    const int lookahead = (G && !G->failed) ? (which == 1 ? 2 : 3) : 1;      // launches in flight beyond the one inspected
+    int result = -1, launched = 0, checked = 0, seen = 0, cond_launched = 0, plain_its = 0, its_queued = 0;
+    std::vector<int> cum;                 // iterations queued up to and including launch i
     bool bad = false;
-    while (result < 0 && !bad && checked < maxit) {
-        while (launched < maxit && launched < checked + 1 + ((G && G->exec && G->conditional) ? lookahead : 1)) {
-            const int it = launched + 1;
+    while (result < 0 && !bad && (checked < launched || its_queued < maxit)) {
+        while (its_queued < maxit && launched < checked + 1 + ((G && G->exec && G->conditional) ? lookahead : 1)) {
             if (G && G->exec) {
                 GL_CUDA(cudaGraphLaunch(G->exec, c->stream));
                 if (G->conditional) { c->launches += 1; cond_launched++; }      // body kernels are counted once we know they ran
                 else c->launches += G->launches;
-            } else if (G && !G->failed && it >= 2) {
+                its_queued += G->its;
+            } else if (G && !G->failed && its_queued >= 1) {
                 // second iteration of the first solve with this configuration: all buffers exist -> capture
                 i64 l0 = c->launches;
-                bool ok = build_pcg_graph(c, G, ring, iteration);
+                bool ok = build_pcg_graph(c, G, ring, iteration, unroll);
                 G->launches = c->launches - l0;
                 c->launches = l0;
-                if (!ok) { G->failed = true; cudaGetLastError(); iteration(); plain_its++; }
+                if (!ok) { G->failed = true; cudaGetLastError(); iteration(); plain_its++; its_queued++; }
                 else {
                     GL_CUDA(cudaGraphLaunch(G->exec, c->stream));
                     if (G->conditional) { c->launches += 1; cond_launched++; } else c->launches += G->launches;
+                    its_queued += G->its;
                 }
-            } else { iteration(); plain_its++; }
+            } else { iteration(); plain_its++; its_queued++; }
             GL_CUDA(cudaEventRecord(ev[launched % NEV], c->stream));
+            cum.push_back(its_queued);
             launched++;
         }
         GL_CUDA(cudaEventSynchronize(ev[checked % NEV]));
+        const int expected = cum[checked];
         checked++;
         // iterations that really ran so far (skipped bodies do not advance the device counter)
-        const int n_done = std::min((int)c->h_ring[64], launched);
+        const int n_done = std::min((int)c->h_ring[64], its_queued);
         for (int k = seen + 1; k <= n_done && result < 0; ++k) {
             const double rr = c->h_ring[(k - 1) & 63];
             if (res_out) *res_out = std::sqrt(rr);
@@ -278,11 +288,12 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
             if (rr <= tol2) result = k;
         }
         seen = n_done;
-        if (n_done < checked && result < 0) bad = true;      // device stopped but the host test did not fire: NaN
+        if (n_done < expected && result < 0) bad = true;      // device stopped but the host test did not fire: NaN
     }
+    if (result > maxit) result = maxit;
     for (auto& e : ev) cudaEventDestroy(e);
     if (G && G->conditional && cond_launched > 0)      // kernels of the conditional bodies that really executed
-        c->launches += (i64)std::max(0, std::min(seen - plain_its, cond_launched)) * (G->launches - 1);
+        c->launches += (i64)std::max(0, std::min((seen - plain_its + G->its - 1) / G->its, cond_launched)) * (G->launches - 1);
     if (recycle) {
         if (result >= 0) {
             // A w = r0 - r_final for the correction w = x (PCG started from zero on r0)
