@@ -59,6 +59,7 @@ struct Amg {
     float* coarse_inv32 = nullptr;
     int coarse_m = 0;
     int cheb_degree = 2;
+    int coarse_degree = 2;      // smoother degree on levels >= 1 (GLIMS_AMG_COARSE_DEGREE)
     double cheb_ratio = 0.1;
 };
 
@@ -783,6 +784,7 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
     }
     Level& lc = amg->L[li + 1];
     const bool l0 = (li == 0);
+    const int degree = l0 ? amg->cheb_degree : amg->coarse_degree;
     float *cur = l.y32, *oth = x;
     double c1, c2;
     {   // pre-smoothing from a zero guess
@@ -793,7 +795,7 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
         else if (l.bs == 3) k_cheb_first32<3><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, l.n, (float)c2);
         else k_cheb_first32<6><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, l.n, (float)c2);
         c->launches++;
-        for (int k = 1; k < amg->cheb_degree; ++k) {
+        for (int k = 1; k < degree; ++k) {
             cc.step(k, c1, c2);
             if (l0) halo_exchange_f32(c, cur, l.bs);
             cheb_step32(c, l, b, cur, oth, (float)c1, (float)c2);
@@ -811,7 +813,7 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
     c->launches++;
     {   // post-smoothing
         ChebCoef cc(l.lmax, amg->cheb_ratio);
-        for (int k = 0; k < amg->cheb_degree; ++k) {
+        for (int k = 0; k < degree; ++k) {
             cc.step(k, c1, c2);
             if (l0) halo_exchange_f32(c, cur, l.bs);
             cheb_step32(c, l, b, cur, oth, (float)c1, (float)c2);
@@ -885,6 +887,8 @@ void amg_setup(glims_ctx* c) {
     amg->dim = D;
     if (const char* e = std::getenv("GLIMS_AMG_DEGREE")) amg->cheb_degree = std::max(1, atoi(e));
     if (const char* e = std::getenv("GLIMS_AMG_RATIO")) amg->cheb_ratio = atof(e);
+    amg->coarse_degree = amg->cheb_degree;
+    if (const char* e = std::getenv("GLIMS_AMG_COARSE_DEGREE")) amg->coarse_degree = std::max(1, atoi(e));
     const int bsc = (D == 2) ? 3 : 6;
     GL_CUDA(cudaStreamSynchronize(c->stream));
 

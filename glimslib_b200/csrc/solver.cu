@@ -193,13 +193,13 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
         if (c->rec_n == 0) state(c).rec_hist.clear();
         launch_copy(c, r, r0, n);
     }
+    static_assert(S_TMP0 == S_BN + 1, "|b|^2 and |r|^2 travel in one message");
     launch_dot(c, b, b, n, S_BN);
-    launch_dot(c, r, r, n, S_TMP3);
-    allreduce_scalars(c, S_BN, 1);
-    allreduce_scalars(c, S_TMP3, 1);
-    double bn2, rn2;
-    read_scalars(c, S_BN, 1, &bn2);
-    read_scalars(c, S_TMP3, 1, &rn2);
+    launch_dot(c, r, r, n, S_TMP0);
+    allreduce_scalars(c, S_BN, 2);
+    double nrm[2];
+    read_scalars(c, S_BN, 2, nrm);
+    const double bn2 = nrm[0], rn2 = nrm[1];
     double bn = std::sqrt(bn2), rn0 = std::sqrt(rn2);
     if (scale <= 0) scale = bn;
     double tol = std::max(tol_rel * scale, tol_abs);
@@ -246,7 +246,8 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
     // cheap iterations (K_cc: one scalar SpMV) are captured several to a body, so that the per-launch cost of the
     // conditional node is amortised; at most unroll-1 extra iterations run after convergence (harmless: alpha and
     // beta guard against 0/0)
-    static const int unroll_c = std::getenv("GLIMS_PCG_UNROLL") ? std::max(1, atoi(std::getenv("GLIMS_PCG_UNROLL"))) : 4;
+    const char* eu = std::getenv("GLIMS_PCG_UNROLL");
+    const int unroll_c = eu ? std::max(1, atoi(eu)) : 4;
     const int unroll = which == 2 ? unroll_c : 1;
     const int lookahead = (G && !G->failed) ? (which == 1 ? 2 : 3) : 1;      // launches in flight beyond the one inspected
     int result = -1, launched = 0, checked = 0, seen = 0, cond_launched = 0, plain_its = 0, its_queued = 0;

@@ -216,8 +216,14 @@ def test_c1_time_loop_matches_oracle(mode):
     eng.close()
 
 
-def test_3d_coupled_steps_match_oracle():
-    """3D two-tissue coupled box (config C3 shrunk to 8^3): 3 steps within 1e-8 relative L2."""
+@pytest.mark.parametrize("env", [{}, {"GLIMS_NO_COND_GRAPH": "1"}, {"GLIMS_NO_GRAPH": "1"}, {"GLIMS_AMG_FP16": "0"},
+                                 {"GLIMS_AMG_FP16": "2"}, {"GLIMS_PCG_UNROLL": "1"}])
+def test_3d_coupled_steps_match_oracle(env, monkeypatch):
+    """3D two-tissue coupled box (config C3 shrunk to 8^3): 3 steps within 1e-8 relative L2 -- with the default solver
+    plumbing (conditional CUDA graphs with the convergence test on the device, FP16 fine-level matrix in the V-cycle,
+    four K_cc iterations per graph body) and with each of those measures switched off / widened."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     coords, cells = meshes.box_mesh((0, 0, 0), (1, 1, 1), 8, 8, 8)
     cm = (coords[cells].mean(axis=1)[:, 0] >= 0.5).astype(np.int32)
     mats = fem.Materials.from_E_nu([3e-3, 1e-3], [0.45, 0.45], [0.002, 0.0], [0.05, 0.0], [0.1, 0.0])
