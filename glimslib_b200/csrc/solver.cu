@@ -864,8 +864,8 @@ int glims_cell_fields(glims_ctx* c, double* cell_out, double* vertex_out) {
 
 int glims_tile_config(glims_ctx* c, int32_t threads_per_cta, int32_t chunk) {
     API_BEGIN
-    if (threads_per_cta != 0 && threads_per_cta != 128 && threads_per_cta != 256)
-        throw GlError(GLIMS_ERR_ARG, "glims_tile_config: threads_per_cta must be 0, 128 or 256");
+    if (threads_per_cta != 0 && threads_per_cta != 128 && threads_per_cta != 192 && threads_per_cta != 256)
+        throw GlError(GLIMS_ERR_ARG, "glims_tile_config: threads_per_cta must be 0, 128, 192 or 256");
     if (chunk < 0) throw GlError(GLIMS_ERR_ARG, "glims_tile_config: chunk must be >= 0");
     GL_CUDA(cudaStreamSynchronize(c->stream));
     tile_free(c);

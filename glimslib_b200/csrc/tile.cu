@@ -78,7 +78,7 @@ k_assemble_tile(const TileArgs A, const TileSmem L) {
         for (int i = tid; i < A.n_mat * TILE_MAT_STRIDE; i += NT) smat[i] = A.mat[i];
     }
     // element records are fetched now (registers) so that their latency overlaps the vertex gathers
-    constexpr int NPRE = 512 / NT;
+    constexpr int NPRE = (512 + NT - 1) / NT;
     unsigned long long tpre[NPRE];
 #pragma unroll
     for (int q = 0; q < NPRE; ++q) {
@@ -194,8 +194,8 @@ static TileDev* tile_ensure(glims_ctx* c) {
     GL_CUDA(cudaMemcpy(col.data(), p.col, sizeof(int) * col.size(), cudaMemcpyDeviceToHost));
     GL_CUDA(cudaMemcpy(cells.data(), c->cells, sizeof(int) * cells.size(), cudaMemcpyDeviceToHost));
     GL_CUDA(cudaMemcpy(cell_mat.data(), c->cell_mat, sizeof(int) * cell_mat.size(), cudaMemcpyDeviceToHost));
-    int nt = c->tile_nt ? c->tile_nt : env_int("GLIMS_TILE_NT", 128);
-    if (nt != 128 && nt != 256) nt = 128;
+    int nt = c->tile_nt ? c->tile_nt : env_int("GLIMS_TILE_NT", 192);
+    if (nt != 128 && nt != 192 && nt != 256) nt = 192;
     const int chunk = std::max(1, c->tile_chunk ? c->tile_chunk : env_int("GLIMS_TILE_CH", 12));
     int hw = (int)std::thread::hardware_concurrency();
     hw = std::max(1, std::min(hw, 32));
@@ -234,6 +234,7 @@ static bool tile_launch_dim(glims_ctx* c, TileDev* t, int what) {
         GL_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
         kfn<<<2 * c->pat.n_slices, NT, L.total, c->stream>>>(A, L); } while (0)
     if (nt == 256) TILE_GO(256, 3);
+    else if (nt == 192) TILE_GO(192, 3);
     else TILE_GO(128, 4);
 #undef TILE_GO
     c->launches++;

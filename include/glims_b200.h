@@ -165,7 +165,7 @@ int glims_cell_fields(glims_ctx* c, double* cell_out, double* vertex_out);
    records, max contributor entries, max items, max partial buffers per slice, shared-memory bytes per CTA, device bytes of
    the maps, threads per CTA.  Returns GLIMS_ERR_STATE when the maps were not built or cannot represent the mesh. */
 int glims_tile_info(glims_ctx* c, int64_t* info8);
-/* Tuning knobs of the tile kernel: threads per CTA (128 or 256; 0 = default 128 / env GLIMS_TILE_NT) and the longest
+/* Tuning knobs of the tile kernel: threads per CTA (128, 192 or 256; 0 = default 192 / env GLIMS_TILE_NT) and the longest
    contributor chunk one warp handles before a column is split (0 = default 12 / env GLIMS_TILE_CH).  Drops the maps;
    they are rebuilt by the next GLIMS_ASMK_TILE assembly. */
 int glims_tile_config(glims_ctx* c, int32_t threads_per_cta, int32_t chunk);
