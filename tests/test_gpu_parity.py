@@ -103,7 +103,7 @@ def test_atomic_and_gather_kernels_agree(d):
 
 
 @pytest.mark.parametrize("d,n", [(2, 40), (3, 12)])
-@pytest.mark.parametrize("nt,chunk", [(128, 12), (256, 8), (128, 5), (256, 100)])
+@pytest.mark.parametrize("nt,chunk", [(128, 12), (256, 8), (192, 5), (192, 100)])
 def test_tile_kernel_all_masks_and_configs(d, n, nt, chunk):
     """Fused tile kernel (GLIMS_ASMK_TILE): every `what` mask leaves exactly the requested outputs equal to the oracle,
     for every CTA size / column-split setting (split columns combine partial sums across warps), on a jittered
