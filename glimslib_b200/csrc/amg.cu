@@ -472,6 +472,33 @@ k_spmv32_row(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
     }
 }
 
+// One component (block-row component i) of y = A x for the slice row `lane`: four block columns in flight, so that a
+// row of ~24 blocks costs ~6 dependent rounds of loads instead of ~12 (the coarse levels are latency bound).
+template <int BS, typename MT>
+__device__ inline float split_row_dot(const i64 base, const int w, const int* __restrict__ col, const MT* __restrict__ A,
+                                      const float* __restrict__ x, const int i, const int lane) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int j = 0;
+    for (; j + 3 < w; j += 4) {
+        int cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cc[u] = __ldg(&col[base + (i64)(j + u) * 32 + lane]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const MT* Au = A + (base + (i64)(j + u) * 32) * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc[u] += ld_mat(&Au[b * 32]) * __ldg(&x[(i64)cc[u] * BS + b]);
+        }
+    }
+    for (; j < w; ++j) {
+        const int c0 = __ldg(&col[base + (i64)j * 32 + lane]);
+        const MT* A0 = A + (base + (i64)j * 32) * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < BS; ++b) acc[0] += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
+    }
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
 // CTA per slice, warp per block-row component (coarse levels, BS = 3|6)
 template <int BS, bool RESID, typename MT>
 __global__ void __launch_bounds__(32 * BS)
@@ -483,28 +510,9 @@ k_spmv32_split(const i64* __restrict__ slice_off, const int* __restrict__ slice_
         const int r = S * 32 + lane;
         const i64 base = slice_off[S];
         const int w = slice_w[S];
-        float acc0 = 0.f, acc1 = 0.f;
-        int j = 0;
-        for (; j + 1 < w; j += 2) {
-            const i64 g0 = base + (i64)j * 32, g1 = g0 + 32;
-            const int c0 = __ldg(&col[g0 + lane]), c1 = __ldg(&col[g1 + lane]);
-            const MT* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
-            const MT* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
-#pragma unroll
-            for (int b = 0; b < BS; ++b) {
-                acc0 += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
-                acc1 += ld_mat(&A1[b * 32]) * __ldg(&x[(i64)c1 * BS + b]);
-            }
-        }
-        if (j < w) {
-            const i64 g0 = base + (i64)j * 32;
-            const int c0 = __ldg(&col[g0 + lane]);
-            const MT* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
-#pragma unroll
-            for (int b = 0; b < BS; ++b) acc0 += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
-        }
+        const float dotv = split_row_dot<BS, MT>(base, w, col, A, x, i, lane);
         if (r < n_rows) {
-            const float v = unscale * (acc0 + acc1);
+            const float v = unscale * dotv;
             y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - v : v;
         }
     }
@@ -592,27 +600,8 @@ k_spmv32_split_cheb(const i64* __restrict__ slice_off, const int* __restrict__ s
         const int r = S * 32 + lane;
         const i64 base = slice_off[S];
         const int w = slice_w[S];
-        float acc0 = 0.f, acc1 = 0.f;
-        int j = 0;
-        for (; j + 1 < w; j += 2) {
-            const i64 g0 = base + (i64)j * 32, g1 = g0 + 32;
-            const int c0 = __ldg(&col[g0 + lane]), c1i = __ldg(&col[g1 + lane]);
-            const MT* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
-            const MT* A1 = A + g1 * (BS * BS) + (i * BS) * 32 + lane;
-#pragma unroll
-            for (int b = 0; b < BS; ++b) {
-                acc0 += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
-                acc1 += ld_mat(&A1[b * 32]) * __ldg(&x[(i64)c1i * BS + b]);
-            }
-        }
-        if (j < w) {
-            const i64 g0 = base + (i64)j * 32;
-            const int c0 = __ldg(&col[g0 + lane]);
-            const MT* A0 = A + g0 * (BS * BS) + (i * BS) * 32 + lane;
-#pragma unroll
-            for (int b = 0; b < BS; ++b) acc0 += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
-        }
-        rs[i][lane] = r < n_rows ? rhs[(i64)r * BS + i] - unscale * (acc0 + acc1) : 0.f;
+        const float dotv = split_row_dot<BS, MT>(base, w, col, A, x, i, lane);
+        rs[i][lane] = r < n_rows ? rhs[(i64)r * BS + i] - unscale * dotv : 0.f;
         __syncthreads();
         if (r < n_rows) {
             float z = 0.f;
@@ -645,16 +634,19 @@ __global__ void k_cheb_update32(const float* __restrict__ dinv, const float* __r
     }
 }
 
+// r_c = P^T r_f.  One warp per aggregate, lanes over its members (about twenty), shuffle reduction: the aggregate's
+// members are visited in one round instead of a serial loop -- these kernels are pure latency on the small levels.
 template <int D>
-__global__ void k_restrict32(int nc, const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx, bool level0,
-                             const double* __restrict__ rvec, const unsigned char* __restrict__ free_mask,
-                             const float* __restrict__ rf, float* __restrict__ rc) {
-    int I = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(TPB)
+k_restrict32(int nc, const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx, bool level0,
+             const double* __restrict__ rvec, const unsigned char* __restrict__ free_mask,
+             const float* __restrict__ rf, float* __restrict__ rc) {
+    const int I = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (I >= nc) return;
     constexpr int NR = (D == 2) ? 1 : 3;
     const int bsc = D + NR, bsf = level0 ? D : bsc;
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int m = mem_ptr[I]; m < mem_ptr[I + 1]; ++m) {
+    for (int m = mem_ptr[I] + lane; m < mem_ptr[I + 1]; m += 32) {
         const int i = mem_idx[m];
         double P[6][6];
         int a_, b_;
@@ -664,7 +656,13 @@ __global__ void k_restrict32(int nc, const int* __restrict__ mem_ptr, const int*
             for (int j = 0; j < bsc; ++j) acc[j] += P[k][j] * v;
         }
     }
-    for (int j = 0; j < bsc; ++j) rc[(i64)I * bsc + j] = (float)acc[j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+        if (lane == j && j < bsc) rc[(i64)I * bsc + j] = (float)acc[j];
 }
 
 template <int D>
@@ -804,8 +802,8 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
     }
     if (l0) halo_exchange_f32(c, cur, l.bs);
     spmv32(c, l, cur, l.r32, b);
-    if (D == 2) k_restrict32<2><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
-    else k_restrict32<3><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
+    if (D == 2) k_restrict32<2><<<nblk(l.nc, TPB / 32), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
+    else k_restrict32<3><<<nblk(l.nc, TPB / 32), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
     c->launches++;
     vcycle32(c, amg, li + 1, lc.b32, lc.x32);
     if (D == 2) k_prolong_add32<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
@@ -1009,6 +1007,12 @@ void amg_setup(glims_ctx* c) {
     for (size_t li = 0; li + 1 < amg->L.size(); ++li) estimate_lmax(c, amg->L[li]);
     GL_CUDA(cudaStreamSynchronize(c->stream));
     build_fp32(c, amg);
+    if (std::getenv("GLIMS_VERBOSE"))
+        for (size_t li = 0; li < amg->L.size(); ++li) {
+            const Level& l = amg->L[li];
+            fprintf(stderr, "glims amg level %zu: %d nodes x %d dofs, %lld blocks (%lld slots, max row %d), lmax %.3f\n", li, l.n, l.bs,
+                    (long long)l.pat.nnzb, (long long)l.pat.n_slots, l.pat.max_w, l.lmax);
+        }
 }
 
 // one fused smoother step on the fine level with the hierarchy's own buffers (roofline bench, glims_time_kernel 6)
