@@ -634,6 +634,29 @@ __global__ void k_cheb_update32(const float* __restrict__ dinv, const float* __r
     }
 }
 
+// thread per aggregate: better for the large fine-level restriction (tens of thousands of aggregates)
+template <int D>
+__global__ void k_restrict32_serial(int nc, const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx, bool level0,
+                             const double* __restrict__ rvec, const unsigned char* __restrict__ free_mask,
+                             const float* __restrict__ rf, float* __restrict__ rc) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nc) return;
+    constexpr int NR = (D == 2) ? 1 : 3;
+    const int bsc = D + NR, bsf = level0 ? D : bsc;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int m = mem_ptr[I]; m < mem_ptr[I + 1]; ++m) {
+        const int i = mem_idx[m];
+        double P[6][6];
+        int a_, b_;
+        build_P<D>(level0, rvec + (i64)i * D, level0 ? free_mask[i] : 0xffu, P, a_, b_);
+        for (int k = 0; k < bsf; ++k) {
+            double v = rf[(i64)i * bsf + k];
+            for (int j = 0; j < bsc; ++j) acc[j] += P[k][j] * v;
+        }
+    }
+    for (int j = 0; j < bsc; ++j) rc[(i64)I * bsc + j] = (float)acc[j];
+}
+
 // r_c = P^T r_f.  One warp per aggregate, lanes over its members (about twenty), shuffle reduction: the aggregate's
 // members are visited in one round instead of a serial loop -- these kernels are pure latency on the small levels.
 template <int D>
@@ -802,7 +825,10 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
     }
     if (l0) halo_exchange_f32(c, cur, l.bs);
     spmv32(c, l, cur, l.r32, b);
-    if (D == 2) k_restrict32<2><<<nblk(l.nc, TPB / 32), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
+    if (l.nc >= 16384) {      // many aggregates: thread per aggregate; few: warp per aggregate (latency)
+        if (D == 2) k_restrict32_serial<2><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
+        else k_restrict32_serial<3><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
+    } else if (D == 2) k_restrict32<2><<<nblk(l.nc, TPB / 32), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
     else k_restrict32<3><<<nblk(l.nc, TPB / 32), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
     c->launches++;
     vcycle32(c, amg, li + 1, lc.b32, lc.x32);
