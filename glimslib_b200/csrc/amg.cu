@@ -615,25 +615,6 @@ k_spmv32_split_cheb(const i64* __restrict__ slice_off, const int* __restrict__ s
     }
 }
 
-template <int BS>
-__global__ void k_cheb_update32(const float* __restrict__ dinv, const float* __restrict__ r, float* __restrict__ d,
-                                float* __restrict__ x, int n, float c1, float c2) {
-    for (i64 row = blockIdx.x * (i64)TPB + threadIdx.x; row < n; row += (i64)gridDim.x * TPB) {
-        float rv[BS];
-#pragma unroll
-        for (int i = 0; i < BS; ++i) rv[i] = r[row * BS + i];
-#pragma unroll
-        for (int i = 0; i < BS; ++i) {
-            float z = 0.f;
-#pragma unroll
-            for (int j = 0; j < BS; ++j) z += dinv[row * BS * BS + i * BS + j] * rv[j];
-            float dn = c2 * z + (c1 != 0.f ? c1 * d[row * BS + i] : 0.f);
-            d[row * BS + i] = dn;
-            x[row * BS + i] += dn;
-        }
-    }
-}
-
 // thread per aggregate: better for the large fine-level restriction (tens of thousands of aggregates)
 template <int D>
 __global__ void k_restrict32_serial(int nc, const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx, bool level0,

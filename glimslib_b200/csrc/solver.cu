@@ -161,7 +161,8 @@ bool build_pcg_graph(glims_ctx* c, PcgGraph* G, double* ring, F&& iteration, int
 }
 
 // PCG on block `which` (1: K_uu, 2: K_cc), zero initial guess. Returns iterations, or -1 if not converged.
-constexpr int REC_KEEP = 10;   // solutions whose span survives a compression
+static int rec_keep_env() { const char* e = std::getenv("GLIMS_REC_KEEP"); int v = e ? atoi(e) : 10; return v < 2 ? 2 : (v > 28 ? 28 : v); }
+#define REC_KEEP (rec_keep_env())   // solutions whose span survives a compression (default 10)
 
 constexpr int REC_M = 30;    // directions kept for the successive-RHS projection (k_multi_dot handles <= 32)
 
