@@ -202,6 +202,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
     read_scalars(c, S_BN, 2, nrm);
     const double bn2 = nrm[0], rn2 = nrm[1];
     double bn = std::sqrt(bn2), rn0 = std::sqrt(rn2);
+    if (which == 1 && std::getenv("GLIMS_VERBOSE")) fprintf(stderr, "glims pcg(u): basis %d, |b| %.3e, |r| after projection %.3e (%.2e of |b|)\n", c->rec_n, bn, rn0, bn > 0 ? rn0 / bn : 0.0);
     if (scale <= 0) scale = bn;
     double tol = std::max(tol_rel * scale, tol_abs);
     if (res_out) *res_out = rn0;
