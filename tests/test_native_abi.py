@@ -39,6 +39,11 @@ def test_null_context_is_an_error_not_a_crash():
     lib = N.load()
     assert lib.glims_set_dt(None, 1.0) == N.ERR_ARG
     assert lib.glims_destroy(None) == N.ERR_ARG
+    # entry points added with the tile-assembly kernel and the peer-memory transport
+    assert lib.glims_tile_config(None, 0, 0) == N.ERR_ARG
+    assert lib.glims_tile_info(None, None) == N.ERR_ARG
+    assert lib.glims_set_p2p(None, 1) == N.ERR_ARG
+    assert lib.glims_comm_bench(None, 0, 1, None) == N.ERR_ARG
 
 
 def test_create_rejects_bad_arguments_before_touching_cuda():
