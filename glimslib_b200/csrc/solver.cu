@@ -161,8 +161,8 @@ bool build_pcg_graph(glims_ctx* c, PcgGraph* G, double* ring, F&& iteration, int
 }
 
 // PCG on block `which` (1: K_uu, 2: K_cc), zero initial guess. Returns iterations, or -1 if not converged.
-static int rec_keep_env() { const char* e = std::getenv("GLIMS_REC_KEEP"); int v = e ? atoi(e) : 10; return v < 2 ? 2 : (v > 28 ? 28 : v); }
-#define REC_KEEP (rec_keep_env())   // solutions whose span survives a compression (default 10)
+// solutions whose span survives a compression of the projection basis (default 10; GLIMS_REC_KEEP)
+inline int rec_keep() { const char* e = std::getenv("GLIMS_REC_KEEP"); int v = e ? atoi(e) : 10; return v < 2 ? 2 : (v > 28 ? 28 : v); }
 
 constexpr int REC_M = 30;    // directions kept for the successive-RHS projection (k_multi_dot handles <= 32)
 
@@ -311,13 +311,13 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
             }
             auto& Ha = state(c).rec_hist;
             if (c->rec_n >= REC_M) {
-                // Basis full: compress it to an A-orthonormal basis of span{last REC_KEEP-1 solutions, the
+                // Basis full: compress it to an A-orthonormal basis of span{last rec_keep()-1 solutions, the
                 // projection part of this one}.  U is A-orthonormal, so Gram-Schmidt on the small coefficient
                 // vectors is Gram-Schmidt in the A-inner product; the new vectors are U * q_i.
                 const int m = c->rec_n;
                 std::vector<std::vector<double>> cand;
                 cand.push_back(std::vector<double>(acur.begin(), acur.begin() + m));
-                for (size_t j = 0; j < Ha.size() && (int)cand.size() < REC_KEEP; ++j)
+                for (size_t j = 0; j < Ha.size() && (int)cand.size() < rec_keep(); ++j)
                     cand.push_back(std::vector<double>(Ha[j].begin(), Ha[j].begin() + m));
                 std::vector<std::vector<double>> Q;
                 for (auto v : cand) {
@@ -328,7 +328,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
                     if (n1 > 1e-20 * n0 && n1 > 0) { double inv = 1.0 / std::sqrt(n1); for (auto& t : v) t *= inv; Q.push_back(v); }
                 }
                 const int kq = (int)Q.size();
-                double *T = ws(c, "rec_T", nl * REC_KEEP), *AT = ws(c, "rec_AT", nl * REC_KEEP), *qd = ws(c, "rec_q", 64);
+                double *T = ws(c, "rec_T", nl * rec_keep()), *AT = ws(c, "rec_AT", nl * rec_keep()), *qd = ws(c, "rec_q", 64);
                 for (int i = 0; i < kq; ++i) {
                     GL_CUDA(cudaMemcpyAsync(qd, Q[i].data(), sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
                     launch_zero(c, T + (i64)i * nl, n);
@@ -348,7 +348,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
                     return o;
                 };
                 for (auto& h : Ha) h = reproject(h);
-                if ((int)Ha.size() > REC_KEEP) Ha.resize(REC_KEEP);
+                if ((int)Ha.size() > rec_keep()) Ha.resize(rec_keep());
                 acur = reproject(acur);
                 c->rec_n = kq;
             }
@@ -376,7 +376,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
                     acur[slot] = std::sqrt(nn);
                 }
                 Ha.insert(Ha.begin(), acur);            // newest first
-                if ((int)Ha.size() > REC_KEEP) Ha.resize(REC_KEEP);
+                if ((int)Ha.size() > rec_keep()) Ha.resize(rec_keep());
             }
         }
         launch_axpy(c, 1.0, xbar, x, n);      // x = x_bar + correction
