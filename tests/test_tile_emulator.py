@@ -145,3 +145,44 @@ def test_tile_emulator_owned_rows_only(emu):
     out = run_emu(emu, sub, x, xp, n_rows=n_own)
     ek, ef = compare(prob, x, xp, out, n_rows=n_own)
     assert ek < 1e-13 and ef < 1e-13, (ek, ef)
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_tile_emulator_single_element_and_tiny_meshes(emu, d):
+    """Edge cases of the maps: one element (a single ragged tile), and a mesh smaller than one tile."""
+    rng = np.random.default_rng(1)
+    if d == 2:
+        coords = np.array([[0.0, 0.0], [1.0, 0.1], [0.2, 0.9]])
+        cells = np.array([[0, 1, 2]], dtype=np.int32)
+    else:
+        coords = np.array([[0.0, 0.0, 0.0], [1.0, 0.1, 0.0], [0.2, 0.9, 0.1], [0.1, 0.2, 0.8]])
+        cells = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    mats = fem.Materials.from_E_nu([3e-3], [0.45], [0.1], [0.2], [0.15])
+    prob = fem.Problem(coords, cells, np.zeros(1, np.int32), mats, dt=0.7)
+    x, xp = rng.standard_normal(prob.ndof), rng.standard_normal(prob.ndof)
+    ek, ef = compare(prob, x, xp, run_emu(emu, prob, x, xp))
+    assert ek < 1e-13 and ef < 1e-13
+    prob, x, xp = problem(d, 2, seed=4)
+    ek, ef = compare(prob, x, xp, run_emu(emu, prob, x, xp))
+    assert ek < 1e-13 and ef < 1e-13
+
+
+@pytest.mark.parametrize("d,n", [(2, 14), (3, 6)])
+def test_tile_emulator_arbitrary_vertex_numbering(emu, d, n):
+    """Unstructured numbering: vertices (and cells) randomly permuted, so a tile's 16 rows are scattered over the mesh,
+    its elements have no translation structure and its local vertex set is large -- the maps must still be exact
+    (element order falls back to a greedy best effort, which only costs bank conflicts)."""
+    prob, x, xp = problem(d, n, seed=8)
+    rng = np.random.default_rng(2)
+    nv = len(prob.coords)
+    perm = rng.permutation(nv)                 # new -> old
+    inv = np.empty(nv, np.int64)
+    inv[perm] = np.arange(nv)
+    cperm = rng.permutation(len(prob.cells))
+    cells2 = np.ascontiguousarray(inv[prob.cells][cperm].astype(np.int32))
+    nb = d + 1
+    p2 = fem.Problem(np.ascontiguousarray(prob.coords[perm]), cells2, np.ascontiguousarray(prob.cell_mat[cperm]), prob.mats, prob.dt)
+    p2.f_ext = prob.f_ext.reshape(nv, nb)[perm].ravel()
+    x2, xp2 = x.reshape(nv, nb)[perm].ravel(), xp.reshape(nv, nb)[perm].ravel()
+    ek, ef = compare(p2, x2, xp2, run_emu(emu, p2, x2, xp2))
+    assert ek < 1e-13 and ef < 1e-13, (ek, ef)
