@@ -120,3 +120,19 @@ def test_structured_mesh_numbering():
     assert cells.tolist() == [[0, 1, 3, 7], [0, 1, 7, 5], [0, 5, 7, 4], [0, 3, 2, 7], [0, 6, 4, 7], [0, 2, 6, 7]]
     _, V = fem.geometry(coords, cells)
     assert np.allclose(V, 1 / 6)
+
+
+def test_amg_partition_study_reproduces_the_multi_gpu_iteration_penalty():
+    """benchmarks/amg_partition_study.py (scipy rebuild of the library's AMG preconditioner): dropping the couplings between
+    the ranks' coarse aggregates costs PCG iterations, keeping them with the same rank-local aggregates does not."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "amg_partition_study.py"), "--grid", "16", "--parts", "4"],
+                         capture_output=True, text=True, timeout=600, check=True)
+    its = json.loads(out.stdout.strip().splitlines()[-1])["pcg_iterations"]
+    assert its["local-drop"] > its["global"]
+    assert its["local-keep"] <= its["global"] + 2
+    assert its["local-keep"] < its["local-drop"]
