@@ -8,6 +8,8 @@ reference (danielabler/glimslib) hands to FEniCS every time step:
 * the physics one-liners  ``glimslib/simulation_helpers/math_linear_elasticity.py:6-17,32-33``
                           ``glimslib/simulation_helpers/math_reaction_diffusion.py:2-3``
 * the time loop           ``glimslib/simulation/simulation_base.py:236-317``
+* (next scope row, N4)    the discrete adjoint of that loop for the controls and misfit of
+                          ``image_based_optimization.py:660-700`` -- :mod:`oracle.adjoint`, checked against finite differences
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it, and only as the checker or as the
