@@ -328,7 +328,7 @@ def main():
                     "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, r01)", "peak_source": peak_src}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # reported at N=1 only
         cpu = cpu_baseline(w["mesh"].num_cells())
 
     if rank == 0:
