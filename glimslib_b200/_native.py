@@ -19,13 +19,14 @@ SYMBOLS = [
     "glims_stream", "glims_step", "glims_assemble", "glims_get_residual", "glims_export_pattern",
     "glims_export_values", "glims_spmv", "glims_time_kernel", "glims_launch_count", "glims_cell_fields",
     "glims_nccl_unique_id", "glims_comm_init", "glims_set_halo", "glims_tile_info", "glims_tile_config", "glims_set_p2p", "glims_comm_bench",
+    "glims_prepare", "glims_reset_history", "glims_set_dof_permutation", "glims_get_dof_permutation",
 ]
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOT_CONVERGED, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5
 ASM_RESIDUAL, ASM_KCONST, ASM_KCC, ASM_JACOBIAN, ASM_ALL = 1, 2, 4, 6, 7
 SOLVER_BLOCK_TRI, SOLVER_MONO_GMRES = 0, 1
 PC_JACOBI, PC_AMG, PC_AMG_FP64 = 0, 1, 2
-ASMK_ATOMIC, ASMK_GATHER, ASMK_SLICE, ASMK_TILE = 0, 1, 2, 3
+ASMK_ATOMIC, ASMK_GATHER, ASMK_SLICE, ASMK_TILE, ASMK_ROWS = 0, 1, 2, 3, 4
 
 
 class SolverOpts(C.Structure):
@@ -93,6 +94,10 @@ def load():
         "glims_tile_config": (i32, [p, i32, i32]),
         "glims_set_p2p": (i32, [p, i32]),
         "glims_comm_bench": (i32, [p, i32, i32, C.POINTER(C.c_float)]),
+        "glims_prepare": (i32, [p, C.POINTER(SolverOpts)]),
+        "glims_reset_history": (i32, [p]),
+        "glims_set_dof_permutation": (i32, [p, lp]),
+        "glims_get_dof_permutation": (i32, [p, lp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

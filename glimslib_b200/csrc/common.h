@@ -99,6 +99,15 @@ struct glims_ctx {
     bool have_slice = false;
     int tile_nt = 0, tile_chunk = 0;   // 0: GLIMS_TILE_NT / GLIMS_TILE_CH or the defaults (glims_tile_config)
     void* tile = nullptr;       // tile.cu: TileDev (maps of the fused tile-assembly kernel), built on first use
+    void* ccmap = nullptr;      // ccrow.cu: CcMap ((row, element) pair lists + per-slot constants of the row-walk assembly)
+    int kuu_state = 0;          // K_uu / K_uc contents: 0 not assembled for the current materials, 1 raw, 2 Dirichlet-eliminated
+    bool bc_nonzero = false;    // some Dirichlet value is non-zero (F_u by SpMV then needs the lift of the eliminated columns)
+    bool lift_dirty = false;    // Dirichlet values changed on an unchanged dof set: K_uu/K_uc must be re-eliminated for the lift
+    bool fu_cache_valid = false;// fu2_cached is |F_u|^2 of the current (x, c, BCs, load): reused as the first residual of the next step
+    double fu2_cached = 0.0;
+    i64* dof_perm = nullptr;            // caller dof numbering -> vertex-blocked (device; null = identity)
+    std::vector<int64_t> h_dof_perm;
+    std::vector<long long> h_bc_dofs;   // host copy of the Dirichlet dof set (to tell a value update from a set change)
 
     // matrices (SELL value layout, see vidx)
     double *Kuu = nullptr, *Kuc = nullptr, *Kcc = nullptr;
@@ -153,6 +162,17 @@ bool launch_assemble_tile(glims_ctx* c, int what);   // false: maps cannot repre
 void tile_free(glims_ctx* c);
 const char* tile_status(glims_ctx* c, long long* info8);
 
+// ---------------- ccrow.cu (row-walk assembly, GLIMS_ASMK_ROWS)
+bool cc_available(glims_ctx* c);                     // builds the pair lists on first use; false: mesh not representable
+const char* cc_status(glims_ctx* c);
+void cc_free(glims_ctx* c);
+void cc_invalidate_consts(glims_ctx* c);             // materials or dt changed
+void cc_mass_cprev(glims_ctx* c);                    // M c_prev of the current u_previous
+bool launch_cc_rows(glims_ctx* c, bool with_kcc, bool with_res);   // K_cc and/or F_c from the current state
+void launch_fu(glims_ctx* c, bool eliminated);       // F_u = K_uu u + K_uc c (+ lift) - f_ext from the stored blocks
+void cc_compute_lift(glims_ctx* c, bool any_nonzero);// while K_uu / K_uc are raw
+i64 cc_map_bytes(glims_ctx* c);
+
 // ---------------- kernels.cu (launch wrappers; all on c->stream)
 void launch_assemble(glims_ctx* c, int what, int variant);
 void launch_bc_values(glims_ctx* c, double* x);
@@ -195,6 +215,7 @@ void launch_split_norms(glims_ctx* c, const double* F, int s0);   // |F_u|^2, |F
 void launch_multi_axpy(glims_ctx* c, const double* V, i64 ld, int k, const double* coef_dev, double sign, double* w, i64 n);
 void read_scalars(glims_ctx* c, int slot0, int n, double* out);   // sync
 void flush_l2(glims_ctx* c);
+void launch_permute(glims_ctx* c, const double* src, double* dst, const i64* perm, i64 n, bool scatter);  // scatter: dst[perm[i]] = src[i]
 
 // ---------------- amg.cu
 void amg_setup(glims_ctx* c);

@@ -3,6 +3,7 @@
 // shuffle reductions (K6).  sm_100a; FP64 throughout; no tensor cores (nothing here is a dense
 // contraction) -- every kernel is bound by HBM traffic or FP64 issue.
 #include "common.h"
+#include "geom.cuh"
 
 namespace {
 
@@ -62,40 +63,6 @@ __device__ inline void grid_reduce(double (&v)[NV], double* partials, unsigned* 
         }
     }
 }
-
-// ------------------------------------------------------------------------------------------------
-// element geometry: barycentric gradients and volume of a P1 simplex
-template <int D> struct Geo { double g[D + 1][D]; double vol; };
-
-__device__ inline void geometry(const double (&X)[3][2], Geo<2>& G) {
-    double j00 = X[1][0] - X[0][0], j01 = X[2][0] - X[0][0];
-    double j10 = X[1][1] - X[0][1], j11 = X[2][1] - X[0][1];
-    double det = j00 * j11 - j01 * j10, id = 1.0 / det;
-    G.g[1][0] = j11 * id;  G.g[1][1] = -j01 * id;
-    G.g[2][0] = -j10 * id; G.g[2][1] = j00 * id;
-    G.g[0][0] = -(G.g[1][0] + G.g[2][0]);
-    G.g[0][1] = -(G.g[1][1] + G.g[2][1]);
-    G.vol = 0.5 * fabs(det);
-}
-__device__ inline void geometry(const double (&X)[4][3], Geo<3>& G) {
-    double e1[3], e2[3], e3[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { e1[k] = X[1][k] - X[0][k]; e2[k] = X[2][k] - X[0][k]; e3[k] = X[3][k] - X[0][k]; }
-    double c1[3] = {e2[1] * e3[2] - e2[2] * e3[1], e2[2] * e3[0] - e2[0] * e3[2], e2[0] * e3[1] - e2[1] * e3[0]};
-    double c2[3] = {e3[1] * e1[2] - e3[2] * e1[1], e3[2] * e1[0] - e3[0] * e1[2], e3[0] * e1[1] - e3[1] * e1[0]};
-    double c3[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-    double det = e1[0] * c1[0] + e1[1] * c1[1] + e1[2] * c1[2], id = 1.0 / det;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        G.g[1][k] = c1[k] * id; G.g[2][k] = c2[k] * id; G.g[3][k] = c3[k] * id;
-        G.g[0][k] = -(G.g[1][k] + G.g[2][k] + G.g[3][k]);
-    }
-    G.vol = fabs(det) * (1.0 / 6.0);
-}
-
-template <int D> struct Consts;
-template <> struct Consts<2> { static constexpr double mass = 1.0 / 12.0; static constexpr double kappa = 1.0 / 60.0; };
-template <> struct Consts<3> { static constexpr double mass = 1.0 / 20.0; static constexpr double kappa = 1.0 / 120.0; };
 
 // ------------------------------------------------------------------------------------------------
 // K1 + K2, element-parallel variant: one thread per element, scatter through the precomputed
@@ -937,6 +904,11 @@ __global__ void k_pcg_cond(cudaGraphConditionalHandle handle, const double* __re
     if (it > 0) go = ring[(it - 1) & 63] > ring[66] ? 1u : 0u;
     cudaGraphSetConditional(handle, go);
 }
+__global__ void k_permute(const double* __restrict__ src, double* __restrict__ dst, const i64* __restrict__ perm, i64 n, bool scatter) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) {
+        if (scatter) dst[perm[i]] = src[i]; else dst[i] = src[perm[i]];
+    }
+}
 __global__ void k_flush(double* buf, i64 n) {
     for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB) buf[i] = (double)i;
 }
@@ -953,6 +925,32 @@ static void assemble_dim(glims_ctx* c, int what, int variant) {
     i64 n_own = c->pat.n_rows;
     const bool res = what & GLIMS_ASM_RESIDUAL, kconst = what & GLIMS_ASM_KCONST, kcc = what & GLIMS_ASM_KCC;
     i64 ns = c->pat.n_slots;
+    if (variant == GLIMS_ASMK_ROWS) {
+        // K_uu / K_uc from the tile kernel (state independent); K_cc and F_c by the row-walk kernel; F_u by SpMV over
+        // the stored blocks, which therefore have to be the raw ones here (glims_step uses the eliminated blocks plus
+        // the lift of the eliminated columns instead, solver.cu)
+        if (!cc_available(c)) {
+            static bool warned = false;
+            if (!warned) { fprintf(stderr, "glims: row-walk assembly unavailable (%s); using the atomic kernel\n", cc_status(c)); warned = true; }
+            variant = GLIMS_ASMK_ATOMIC;
+        } else {
+            if (kconst || (res && c->kuu_state != 1)) {
+                assemble_dim<D>(c, GLIMS_ASM_KCONST, GLIMS_ASMK_TILE);
+                if (!kconst) c->kconst_valid = false;      // the solver's eliminated copy is gone
+            }
+            if (res || kcc) {
+                if (res) {
+                    if (c->halo.active)
+                        GL_CUDA(cudaMemsetAsync(c->F + n_own * NB, 0, sizeof(double) * (c->n_v - n_own) * NB, c->stream));
+                    cc_mass_cprev(c);
+                }
+                launch_cc_rows(c, kcc, res);
+                if (res) launch_fu(c, false);
+            }
+            return;
+        }
+    }
+    if (kconst) c->kuu_state = 1;
     if (variant == GLIMS_ASMK_TILE) {
         // fused residual + Jacobian, one CTA per slice; writes every owned row of F and every slot (no zero-fill)
         if (res && c->halo.active)
@@ -1206,6 +1204,10 @@ void launch_pcg_shift(glims_ctx* c, double* ring) {
 }
 void launch_pcg_cond(glims_ctx* c, unsigned long long handle, const double* ring) {
     k_pcg_cond<<<1, 1, 0, c->stream>>>((cudaGraphConditionalHandle)handle, ring);
+    LAUNCHED(c);
+}
+void launch_permute(glims_ctx* c, const double* src, double* dst, const i64* perm, i64 n, bool scatter) {
+    k_permute<<<red_grid(c, n), TPB, 0, c->stream>>>(src, dst, perm, n, scatter);
     LAUNCHED(c);
 }
 void flush_l2(glims_ctx* c) {

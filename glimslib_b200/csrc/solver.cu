@@ -282,8 +282,12 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
         GL_CUDA(cudaEventSynchronize(ev[checked % NEV]));
         const int expected = cum[checked];
         checked++;
-        // iterations that really ran so far (skipped bodies do not advance the device counter)
-        const int n_done = std::min((int)c->h_ring[64], its_queued);
+        // Iterations that really ran (skipped bodies do not advance the device counter), but never beyond the launch
+        // whose event was just waited for: what a later, still running launch may already have mirrored must not enter
+        // the decision, or ranks whose hosts poll at different moments would stop at different iterations and leave
+        // unmatched halo exchanges / allreduces behind.  r.r is all-reduced, so with this bound every rank sees the
+        // same sequence and queues the same number of launches.
+        const int n_done = std::min((int)c->h_ring[64], expected);
         for (int k = seen + 1; k <= n_done && result < 0; ++k) {
             const double rr = c->h_ring[(k - 1) & 63];
             if (res_out) *res_out = std::sqrt(rr);
@@ -473,16 +477,41 @@ int gmres_mono(glims_ctx* c, const double* b, double* x, double tol, int maxit, 
     return -1;
 }
 
+// The row-walk assembly (GLIMS_ASMK_ROWS) is the default of the block-triangular solver; it needs the pair lists
+// (cc_available) and, for F_u by SpMV, K_uu / K_uc assembled.  Anything else falls back to the element kernels.
+bool use_rows(glims_ctx* c, const glims_solver_opts* o) {
+    return o->asm_kernel == GLIMS_ASMK_ROWS && cc_available(c);
+}
+int kconst_kernel(glims_ctx* c, const glims_solver_opts* o) {
+    return o->asm_kernel == GLIMS_ASMK_ROWS ? GLIMS_ASMK_TILE : o->asm_kernel;
+}
+
 void ensure_kconst(glims_ctx* c, const glims_solver_opts* o) {
     bool need_amg = (o->pc == GLIMS_PC_AMG || o->pc == GLIMS_PC_AMG_FP64) && o->solver == GLIMS_SOLVER_BLOCK_TRI;
+    const bool rows = use_rows(c, o);
     if (!c->kconst_valid) {
-        launch_assemble(c, GLIMS_ASM_KCONST, o->asm_kernel);
+        launch_assemble(c, GLIMS_ASM_KCONST, kconst_kernel(c, o));
+        if (rows) cc_compute_lift(c, c->bc_nonzero);
         launch_bc_matrix(c, GLIMS_ASM_KCONST, true);
         launch_diag_inverse(c, 1);
         c->kconst_valid = true;
+        c->kuu_state = 3;
+        c->lift_dirty = false;
         c->rec_n = c->rec_head = 0;
         free_graphs(c);
         if (c->amg) amg_free(c);
+    } else if (c->lift_dirty) {
+        // Dirichlet VALUES changed on an unchanged dof set (time-dependent boundary data, helper_classes.py
+        // time_update_bcs): the eliminated matrices, the AMG hierarchy, the captured graphs and the projection basis all
+        // stay valid (symmetric elimination depends on the constrained set only).  Only the lift K_raw(:, bc) g of the
+        // SpMV residual needs the raw columns once more.
+        if (rows && (c->bc_nonzero || c->kuu_state != 3)) {
+            launch_assemble(c, GLIMS_ASM_KCONST, kconst_kernel(c, o));
+            cc_compute_lift(c, c->bc_nonzero);
+            launch_bc_matrix(c, GLIMS_ASM_KCONST, true);
+            c->kuu_state = 3;
+        }
+        c->lift_dirty = false;
     }
     if (need_amg && !c->amg) amg_setup(c);
 }
@@ -493,26 +522,72 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
     const int D = c->dim, NB = c->nb;
     const i64 nr = nrows(c);
     ensure_kconst(c, o);
+    const bool rows = use_rows(c, o);
+    const bool mono = o->solver == GLIMS_SOLVER_MONO_GMRES;
+    const int ek = rows ? GLIMS_ASMK_ATOMIC : o->asm_kernel;      // element kernel for the rare K_cc-only re-assembly
     launch_bc_values(c, c->x);
     double *Fu = ws(c, "Fu", c->n_v * D), *Fc = ws(c, "Fc", c->n_v);
     double *du = ws(c, "du", c->n_v * D), *dc = ws(c, "dc", c->n_v), *tmpu = ws(c, "tmpu", c->n_v * D);
     glims_step_stats s;
     memset(&s, 0, sizeof s);
     double f0 = -1, fu_scale = 0, T = 0;
+    double fu2 = 0.0;                   // |F_u|^2 of the last evaluation
+    bool fu_current = false;            // F's displacement rows belong to the current iterate
     bool converged = false, c_was_done = false;
-    for (int k = 0; k <= o->max_newton; ++k) {
+    if (rows) {
         tm.begin(1);
-        halo_exchange(c, c->x, NB);
-        // one pass over the elements: residual, plus K_cc while the concentration block is still iterating
-        const bool with_kcc = o->solver == GLIMS_SOLVER_MONO_GMRES || !(o->lag_mechanics && c_was_done);
-        launch_assemble(c, GLIMS_ASM_RESIDUAL | (with_kcc ? GLIMS_ASM_KCC : 0), o->asm_kernel);
+        cc_mass_cprev(c);               // M c_prev: constant during the step
+        tm.end(1);
+    }
+    // displacement rows of the residual, row-walk path: one SpMV over the stored (eliminated) blocks + the lift
+    auto eval_fu = [&]() {
+        launch_fu(c, true);
         launch_bc_residual(c, c->F, c->x);
         launch_split_norms(c, c->F, S_TMP0);
         allreduce_scalars(c, S_TMP0, 2);
-        tm.end(1);
         double nn[2];
         read_scalars(c, S_TMP0, 2, nn);
-        double fu = std::sqrt(nn[0]), fc = std::sqrt(nn[1]), fn = std::sqrt(nn[0] + nn[1]);
+        fu2 = nn[0];
+        fu_current = true;
+        c->fu2_cached = fu2; c->fu_cache_valid = true;
+    };
+    for (int k = 0; k <= o->max_newton; ++k) {
+        tm.begin(1);
+        halo_exchange(c, c->x, NB);
+        // one pass: residual, plus K_cc while the concentration block is still iterating
+        const bool with_kcc = mono || !(o->lag_mechanics && c_was_done);
+        double fu, fc, fn;
+        bool fu_known = true;           // fn contains the displacement rows of THIS iterate (evaluated, or cached at k = 0)
+        if (rows) {
+            // concentration rows first (F_c, K_cc); the displacement rows cost an SpMV over K_uu/K_uc and are evaluated
+            // only when the decision needs them: at the first iterate (unless the previous step's final residual still
+            // describes this state), when |F_c| is within the tolerance, and whenever mechanics is not lagged
+            launch_cc_rows(c, with_kcc, true);
+            launch_bc_residual(c, c->F, c->x);
+            launch_split_norms(c, c->F, S_TMP0);
+            allreduce_scalars(c, S_TMP0, 2);
+            double nn[2];
+            read_scalars(c, S_TMP0, 2, nn);
+            fc = std::sqrt(nn[1]);
+            fu_current = false;
+            const bool reuse = (k == 0 && c->fu_cache_valid && !mono && o->lag_mechanics);
+            const bool need_fu = mono || !o->lag_mechanics || (k == 0 ? !reuse : fc <= T);
+            if (need_fu) eval_fu();
+            else if (reuse) fu2 = c->fu2_cached;
+            fu_known = need_fu || reuse;
+            fu = std::sqrt(fu2);
+            fn = std::sqrt(fu2 + nn[1]);
+        } else {
+            launch_assemble(c, GLIMS_ASM_RESIDUAL | (with_kcc ? GLIMS_ASM_KCC : 0), o->asm_kernel);
+            launch_bc_residual(c, c->F, c->x);
+            launch_split_norms(c, c->F, S_TMP0);
+            allreduce_scalars(c, S_TMP0, 2);
+            double nn[2];
+            read_scalars(c, S_TMP0, 2, nn);
+            fu = std::sqrt(nn[0]); fc = std::sqrt(nn[1]); fn = std::sqrt(nn[0] + nn[1]);
+            fu_current = true;
+        }
+        tm.end(1);
         if (!(fn == fn)) throw GlError(GLIMS_ERR_NOT_CONVERGED, "Newton: residual is NaN");
         if (k == 0) {
             f0 = fn; s.fnorm0 = fn;
@@ -528,13 +603,15 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
         }
         s.fnorm = fn;
         s.newton_its = k;
-        if (fn < o->snes_atol || fn <= o->snes_rtol * f0) { converged = true; break; }
+        // the stopping test is on the whole residual; an iterate whose displacement rows were skipped has |F_c| > T
+        if (fu_known && (fn < o->snes_atol || fn <= o->snes_rtol * f0)) { converged = true; break; }
         if (k == o->max_newton) break;
 
         tm.begin(2);
         // monolithic update: GMRES(30) on J with block-Jacobi; also the fallback when a block solve breaks down
         // (e.g. K_cc indefinite for dt*rho > 1, where PCG is not applicable but the reference's GMRES still is)
         auto mono_update = [&](bool kcc_eliminated) {
+            if (rows && !fu_current) eval_fu();
             if (!kcc_eliminated) launch_bc_matrix(c, GLIMS_ASM_KCC, true);
             launch_diag_inverse(c, 0);
             double* rhs = ws(c, "rhs_mono", c->ndof);
@@ -546,16 +623,21 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
             s.krylov_its_mono += its;
             launch_axpy(c, 1.0, c->dx, c->x, nr * NB);
         };
-        if (o->solver == GLIMS_SOLVER_MONO_GMRES) {
+        auto assemble_kcc_only = [&]() {
+            if (rows) launch_cc_rows(c, true, false); else launch_assemble(c, GLIMS_ASM_KCC, ek);
+        };
+        c->fu_cache_valid = false;          // the iterate is about to change
+        if (mono) {
             mono_update(false);
         } else {
-            launch_extract(c, c->F, Fu, Fc);
             const bool c_done = fc <= 0.5 * T;
             c_was_done = c_was_done || c_done;
             const bool solve_c = fc > 0.0 && (!c_done || !o->lag_mechanics);
             const bool solve_u_now = c_done || !o->lag_mechanics;
+            if (rows && solve_u_now && !fu_current) { eval_fu(); fu = std::sqrt(fu2); }
+            launch_extract(c, c->F, solve_u_now ? Fu : nullptr, Fc);
             bool broke = false, kcc_elim = false;
-            if (solve_c && !with_kcc) launch_assemble(c, GLIMS_ASM_KCC, o->asm_kernel);
+            if (solve_c && !with_kcc) assemble_kcc_only();
             if (solve_c) {
                 kcc_elim = true;
                 launch_bc_matrix(c, GLIMS_ASM_KCC, true);
@@ -566,7 +648,7 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
                 if (its < 0) broke = true; else s.krylov_its_c += its;
             } else launch_zero(c, dc, nr);
             if (broke) {
-                if (!with_kcc && !solve_c) launch_assemble(c, GLIMS_ASM_KCC, o->asm_kernel);
+                if (!with_kcc && !solve_c) assemble_kcc_only();
                 mono_update(kcc_elim);
             } else if (solve_u_now && fu > 0.0) {
                 // rhs_u = -F_u - K_uc dc
@@ -580,7 +662,7 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
                 int its = pcg(c, 1, o->pc, Fu, du, o->ksp_rtol, fu_scale, o->ksp_atol, o->max_krylov, &res, o->recycle != 0);
                 if (its < 0) {
                     // K_uu PCG broke down: take the monolithic update instead (needs the current K_cc)
-                    if (!with_kcc && !solve_c) launch_assemble(c, GLIMS_ASM_KCC, o->asm_kernel);
+                    if (!with_kcc && !solve_c) assemble_kcc_only();
                     mono_update(kcc_elim);
                 } else {
                     s.krylov_its_u += its;
@@ -596,7 +678,7 @@ void newton_step(glims_ctx* c, const glims_solver_opts* o, glims_step_stats* st)
     s.ms_assembly = tm.total(1);
     s.ms_krylov = tm.total(2);
     if (st) *st = s;
-    if (!converged) throw GlError(GLIMS_ERR_NOT_CONVERGED, "Newton did not converge");
+    if (!converged) { c->fu_cache_valid = false; throw GlError(GLIMS_ERR_NOT_CONVERGED, "Newton did not converge"); }
 }
 
 }  // namespace
@@ -612,7 +694,7 @@ extern "C" {
 void glims_default_opts(glims_solver_opts* o) {
     o->snes_rtol = 1e-9; o->snes_atol = 1e-10; o->snes_stol = 1e-16; o->max_newton = 50;
     o->ksp_rtol = 1e-10; o->ksp_atol = 1e-300; o->max_krylov = 20000;
-    o->solver = GLIMS_SOLVER_BLOCK_TRI; o->pc = GLIMS_PC_AMG; o->asm_kernel = GLIMS_ASMK_ATOMIC;
+    o->solver = GLIMS_SOLVER_BLOCK_TRI; o->pc = GLIMS_PC_AMG; o->asm_kernel = GLIMS_ASMK_ROWS;
     o->lag_mechanics = 1;
     o->recycle = 1;
     o->extrapolate = 0;
@@ -667,6 +749,7 @@ int glims_destroy(glims_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->amg) amg_free(c);
     tile_free(c);
+    cc_free(c);
     comm_free(c);
     free_pool(c);
     auto& p = c->pat;
@@ -675,7 +758,7 @@ int glims_destroy(glims_ctx* c) {
                     (void*)c->gent, (void*)c->Kuu, (void*)c->Kuc, (void*)c->Kcc, (void*)c->dinv_uu, (void*)c->dinv_cc,
                     (void*)c->dinv_mono, (void*)c->x, (void*)c->xprev, (void*)c->F, (void*)c->fext, (void*)c->dx,
                     (void*)c->bc_dofs, (void*)c->bc_vals, (void*)c->bcmask, (void*)c->scal, (void*)c->partials,
-                    (void*)c->tickets, (void*)c->flush_buf, (void*)c->sl_ptr, (void*)c->sl_elem, (void*)c->lent, (void*)c->halo.send_idx, (void*)c->halo.send_buf})
+                    (void*)c->tickets, (void*)c->flush_buf, (void*)c->sl_ptr, (void*)c->sl_elem, (void*)c->lent, (void*)c->halo.send_idx, (void*)c->halo.send_buf, (void*)c->dof_perm})
         if (q) cudaFree(q);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_ring) cudaFreeHost(c->h_ring);
@@ -698,25 +781,56 @@ int glims_set_materials(glims_ctx* c, int32_t n_mat, const double* table) {
     c->mat = dev_upload(t.data(), (i64)t.size(), c->stream);
     GL_CUDA(cudaStreamSynchronize(c->stream));
     c->n_mat = n_mat; c->have_mat = true; c->kconst_valid = false;
+    c->kuu_state = 0; c->fu_cache_valid = false;
+    cc_invalidate_consts(c);
     API_END
 }
 
-int glims_set_dt(glims_ctx* c, double dt) { if (!c) return GLIMS_ERR_ARG; c->dt = dt; return GLIMS_OK; }
+int glims_set_dt(glims_ctx* c, double dt) {
+    if (!c) return GLIMS_ERR_ARG;
+    if (dt != c->dt) cc_invalidate_consts(c);      // Klin = (1 - dt rho) M + dt D K depends on dt
+    c->dt = dt;
+    return GLIMS_OK;
+}
 
 int glims_set_dirichlet(glims_ctx* c, int64_t n, const int64_t* dofs, const double* vals) {
     API_BEGIN
     if (n < 0 || (n > 0 && (!dofs || !vals))) throw GlError(GLIMS_ERR_ARG, "set_dirichlet: bad arguments");
+    for (i64 t = 0; t < n; ++t)
+        if (dofs[t] < 0 || dofs[t] >= c->ndof) throw GlError(GLIMS_ERR_ARG, "set_dirichlet: dof out of range");
+    std::vector<int64_t> mapped;
+    if (!c->h_dof_perm.empty()) {           // caller numbering -> vertex-blocked
+        mapped.resize(n);
+        for (i64 t = 0; t < n; ++t) mapped[t] = c->h_dof_perm[dofs[t]];
+        dofs = mapped.data();
+    }
+    bool nonzero = false;
+    for (i64 t = 0; t < n; ++t) nonzero = nonzero || vals[t] != 0.0;
+    c->fu_cache_valid = false;
+    // Same constrained set as before: only the values change (time-dependent boundary data).  Symmetric elimination
+    // depends on the set alone, so K_uu / K_uc, the AMG hierarchy, the captured graphs and the projection basis stay.
+    const bool same_set = (i64)c->h_bc_dofs.size() == n && c->n_bc == n &&
+                          std::equal(c->h_bc_dofs.begin(), c->h_bc_dofs.end(), (const long long*)dofs);
+    if (same_set && n > 0) {
+        GL_CUDA(cudaMemcpyAsync(c->bc_vals, vals, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        GL_CUDA(cudaStreamSynchronize(c->stream));
+        if (nonzero || c->bc_nonzero) c->lift_dirty = true;
+        c->bc_nonzero = nonzero;
+        return GLIMS_OK;
+    }
+    if (same_set) return GLIMS_OK;      // still no Dirichlet condition
     if (c->bc_dofs) { cudaFree(c->bc_dofs); c->bc_dofs = nullptr; }
     if (c->bc_vals) { cudaFree(c->bc_vals); c->bc_vals = nullptr; }
     std::vector<unsigned char> mask(c->n_v, 0);
     c->n_bc_u = c->n_bc_c = 0;
     for (i64 t = 0; t < n; ++t) {
-        if (dofs[t] < 0 || dofs[t] >= c->ndof) throw GlError(GLIMS_ERR_ARG, "set_dirichlet: dof out of range");
         i64 v = dofs[t] / c->nb; int k = (int)(dofs[t] - v * c->nb);
         mask[v] |= (unsigned char)(1u << k);
         if (k < c->dim) c->n_bc_u++; else c->n_bc_c++;
     }
     c->n_bc = n;
+    c->h_bc_dofs.assign((const long long*)dofs, (const long long*)dofs + n);
+    c->bc_nonzero = nonzero;
     if (n > 0) {
         c->bc_dofs = dev_upload((const i64*)dofs, n, c->stream);
         c->bc_vals = dev_upload(vals, n, c->stream);
@@ -727,24 +841,41 @@ int glims_set_dirichlet(glims_ctx* c, int64_t n, const int64_t* dofs, const doub
     API_END
 }
 
+static int copy_vec(glims_ctx* c, double* dev, double* host_out, const double* host_in);
+
 int glims_set_load(glims_ctx* c, const double* f_ext) {
     API_BEGIN
     c->have_load = f_ext != nullptr;
+    c->fu_cache_valid = false;
     if (f_ext) {
-        GL_CUDA(cudaMemcpyAsync(c->fext, f_ext, sizeof(double) * c->ndof, cudaMemcpyHostToDevice, c->stream));
-        GL_CUDA(cudaStreamSynchronize(c->stream));
+        int rc = copy_vec(c, c->fext, nullptr, f_ext);
+        if (rc != GLIMS_OK) return rc;
     }
     API_END
 }
 
+// Host <-> device copy of an ndof vector in the CALLER's dof numbering (glims_set_dof_permutation; identity by default)
 static int copy_vec(glims_ctx* c, double* dev, double* host_out, const double* host_in) {
     API_BEGIN
-    if (host_in) GL_CUDA(cudaMemcpyAsync(dev, host_in, sizeof(double) * c->ndof, cudaMemcpyHostToDevice, c->stream));
-    if (host_out) GL_CUDA(cudaMemcpyAsync(host_out, dev, sizeof(double) * c->ndof, cudaMemcpyDeviceToHost, c->stream));
+    const size_t nbytes = sizeof(double) * c->ndof;
+    if (!c->dof_perm) {
+        if (host_in) GL_CUDA(cudaMemcpyAsync(dev, host_in, nbytes, cudaMemcpyHostToDevice, c->stream));
+        if (host_out) GL_CUDA(cudaMemcpyAsync(host_out, dev, nbytes, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        double* stage = ws(c, "perm_stage", c->ndof);
+        if (host_in) {
+            GL_CUDA(cudaMemcpyAsync(stage, host_in, nbytes, cudaMemcpyHostToDevice, c->stream));
+            launch_permute(c, stage, dev, c->dof_perm, c->ndof, true);       // dev[perm[i]] = stage[i]
+        }
+        if (host_out) {
+            launch_permute(c, dev, stage, c->dof_perm, c->ndof, false);      // stage[i] = dev[perm[i]]
+            GL_CUDA(cudaMemcpyAsync(host_out, stage, nbytes, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
     GL_CUDA(cudaStreamSynchronize(c->stream));
     API_END
 }
-int glims_set_state(glims_ctx* c, const double* x) { if (c) c->have_hist = false; return x ? copy_vec(c, c ? c->x : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
+int glims_set_state(glims_ctx* c, const double* x) { if (c) { c->have_hist = false; c->fu_cache_valid = false; } return x ? copy_vec(c, c ? c->x : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
 int glims_get_state(glims_ctx* c, double* x) { return x ? copy_vec(c, c ? c->x : nullptr, x, nullptr) : GLIMS_ERR_ARG; }
 int glims_set_prev(glims_ctx* c, const double* x) { if (c) c->have_hist = false; return x ? copy_vec(c, c ? c->xprev : nullptr, nullptr, x) : GLIMS_ERR_ARG; }
 int glims_get_prev(glims_ctx* c, double* x) { return x ? copy_vec(c, c ? c->xprev : nullptr, x, nullptr) : GLIMS_ERR_ARG; }
@@ -767,12 +898,14 @@ int glims_step(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, glims_
         if (o->extrapolate && c->have_hist) {
             // first Newton guess: c_n + (c_n - c_{n-1}); only the start of the iteration changes, not its fixed point
             launch_extrapolate_c(c, c->x, ws(c, "x_hist", c->ndof));
+            c->fu_cache_valid = false;
         }
         try {
             newton_step(c, o, stats ? &stats[s] : nullptr);
         } catch (const GlError&) {
             launch_copy(c, backup, c->x, c->ndof);
             cudaStreamSynchronize(c->stream);
+            c->fu_cache_valid = false;
             throw;
         }
         // u_previous.assign(solution)  (simulation_base.py:312); ghosts refreshed first so that the next
@@ -787,6 +920,52 @@ int glims_step(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, glims_
     API_END
 }
 
+int glims_prepare(glims_ctx* c, const glims_solver_opts* o) {
+    API_BEGIN
+    if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_prepare before glims_set_materials");
+    glims_solver_opts od;
+    if (!o) { glims_default_opts(&od); o = &od; }
+    ensure_kconst(c, o);
+    if (use_rows(c, o)) cc_mass_cprev(c);        // also builds the per-slot constants
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_reset_history(glims_ctx* c) {
+    API_BEGIN
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    c->rec_n = c->rec_head = 0;
+    if (c->solver_state) state(c).rec_hist.clear();
+    c->have_hist = false;
+    c->fu_cache_valid = false;
+    API_END
+}
+
+int glims_set_dof_permutation(glims_ctx* c, const int64_t* perm) {
+    API_BEGIN
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->dof_perm) { cudaFree(c->dof_perm); c->dof_perm = nullptr; }
+    c->h_dof_perm.clear();
+    if (perm) {
+        std::vector<char> seen(c->ndof, 0);
+        for (i64 i = 0; i < c->ndof; ++i) {
+            if (perm[i] < 0 || perm[i] >= c->ndof || seen[perm[i]]) throw GlError(GLIMS_ERR_ARG, "set_dof_permutation: not a permutation of [0, ndof)");
+            seen[perm[i]] = 1;
+        }
+        if (c->n_bc > 0) throw GlError(GLIMS_ERR_STATE, "set_dof_permutation: call before glims_set_dirichlet");
+        c->h_dof_perm.assign(perm, perm + c->ndof);
+        c->dof_perm = dev_upload((const i64*)perm, c->ndof, c->stream);
+        GL_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    API_END
+}
+
+int glims_get_dof_permutation(glims_ctx* c, int64_t* perm) {
+    if (!c || !perm) return GLIMS_ERR_ARG;
+    for (i64 i = 0; i < c->ndof; ++i) perm[i] = c->h_dof_perm.empty() ? i : c->h_dof_perm[i];
+    return GLIMS_OK;
+}
+
 int glims_assemble(glims_ctx* c, int32_t what, int32_t kernel, int32_t apply_bc) {
     API_BEGIN
     if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_assemble before glims_set_materials");
@@ -798,6 +977,8 @@ int glims_assemble(glims_ctx* c, int32_t what, int32_t kernel, int32_t apply_bc)
     }
     if (what & GLIMS_ASM_KCONST) {
         c->kconst_valid = (apply_bc == 2);
+        if (apply_bc) c->kuu_state = apply_bc == 2 ? 3 : 2;
+        c->lift_dirty = true;           // no lift was computed for these matrices: glims_step rebuilds it if it needs one
         if (c->kconst_valid) launch_diag_inverse(c, 1);
         free_graphs(c);
         c->rec_n = 0;
@@ -898,10 +1079,14 @@ int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t rep
             case 3: launch_spmv(c, 2, dx, dy); break;
             case 4: launch_assemble(c, GLIMS_ASM_RESIDUAL, variant); break;
             case 5: launch_assemble(c, GLIMS_ASM_RESIDUAL | GLIMS_ASM_KCC, variant); break;
+            case 7: launch_cc_rows(c, true, true); break;
+            case 8: launch_fu(c, false); break;
             case 6: if (!amg_time_fine_step(c)) throw GlError(GLIMS_ERR_STATE, "glims_time_kernel 6: no AMG hierarchy yet (run a step with pc = GLIMS_PC_AMG first)"); break;
             default: throw GlError(GLIMS_ERR_ARG, "glims_time_kernel: unknown kernel");
         }
     };
+    if (kernel == 7) { if (!cc_available(c)) throw GlError(GLIMS_ERR_STATE, std::string("glims_time_kernel 7: ") + cc_status(c)); cc_mass_cprev(c); }
+    if (kernel == 8 && c->kuu_state == 0) launch_assemble(c, GLIMS_ASM_KCONST, GLIMS_ASMK_TILE);
     for (int w = 0; w < 3; ++w) run();
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
@@ -917,7 +1102,8 @@ int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t rep
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     *ms_avg = tot / reps;
-    if (kernel == 0) c->kconst_valid = false;   // raw matrices: no Dirichlet elimination applied
+    if (kernel == 0 || kernel == 8) c->kconst_valid = false;   // raw matrices: no Dirichlet elimination applied
+    c->fu_cache_valid = false;
     API_END
 }
 

@@ -117,7 +117,32 @@ class Engine:
     def get_prev(self):
         return self._vec(self._lib.glims_get_prev, "get_prev")
 
+    def set_dof_permutation(self, perm):
+        """Caller dof numbering: ``perm[i]`` = vertex-blocked index ``v*(dim+1)+k`` of the caller's dof ``i`` (e.g. from
+        DOLFIN's ``vertex_to_dof_map``); ``None`` restores the identity.  Call before :meth:`set_dirichlet`."""
+        if perm is None:
+            self._check(self._lib.glims_set_dof_permutation(self._h, None), "set_dof_permutation")
+            return
+        a = np.ascontiguousarray(perm, dtype=np.int64)
+        assert a.size == self.ndof
+        self._check(self._lib.glims_set_dof_permutation(self._h, N.as_lp(a)), "set_dof_permutation")
+
+    def get_dof_permutation(self):
+        out = np.empty(self.ndof, dtype=np.int64)
+        self._check(self._lib.glims_get_dof_permutation(self._h, N.as_lp(out)), "get_dof_permutation")
+        return out
+
     # -- hot path -----------------------------------------------------------------------------
+    def prepare(self, **opts):
+        """One-time work of the first step (K_uu / K_uc, Dirichlet elimination, AMG hierarchy, row-walk maps)."""
+        for k, v in opts.items():
+            setattr(self.opts, k, v)
+        self._check(self._lib.glims_prepare(self._h, C.byref(self.opts)), "prepare")
+
+    def reset_history(self):
+        """Drop the projection basis / extrapolation history (matrices, hierarchy and graphs stay)."""
+        self._check(self._lib.glims_reset_history(self._h), "reset_history")
+
     def step(self, n_steps=1, **opts):
         """``n_steps`` x (Newton-Krylov solve + ``u_previous.assign``). Returns per-step stats dicts."""
         for k, v in opts.items():

@@ -83,6 +83,99 @@ def c4_ellipsoid(n=148):
                  labels=label)
 
 
+def c5_ellipsoid(n=252):
+    """Config C5's mesh size on the C4 geometry: n=252 gives 50.3M tetrahedra / 8.6M vertices."""
+    w = c4_ellipsoid(n)
+    w["name"] = "C5 3D voxel ellipsoid n=%d (50M-tet class) three tissues coupled" % n
+    return w
+
+
+# ---- vertex / cell renumbering (unstructured-ordering studies and the library's locality reorder) ------------------
+def renumber(w, new_of_old, cell_order=None):
+    """Workload ``w`` with vertex ``v`` renamed ``new_of_old[v]`` (and cells listed in ``cell_order``)."""
+    mesh = w["mesh"]
+    nb = mesh.dim + 1
+    new_of_old = np.asarray(new_of_old, dtype=np.int64)
+    old_of_new = np.empty_like(new_of_old)
+    old_of_new[new_of_old] = np.arange(len(new_of_old))
+    cells = new_of_old[mesh.cells].astype(np.int32)
+    cell_mat = w["cell_mat"]
+    if cell_order is not None:
+        cells, cell_mat = cells[cell_order], cell_mat[cell_order]
+    m2 = M.SimplexMesh(mesh.coords[old_of_new], cells)
+    bv = getattr(mesh, "_boundary_vertices", None)
+    if bv is not None:
+        m2._boundary_vertices = np.sort(new_of_old[bv])
+    v, k = w["bc_dofs"] // nb, w["bc_dofs"] % nb
+    dofs = new_of_old[v] * nb + k
+    o = np.argsort(dofs, kind="stable")
+    out = dict(w)
+    out.update(mesh=m2, cell_mat=np.ascontiguousarray(cell_mat, dtype=np.int32), bc_dofs=dofs[o].astype(np.int64),
+               bc_vals=np.asarray(w["bc_vals"])[o], x0=np.ascontiguousarray(w["x0"].reshape(-1, nb)[old_of_new].ravel()),
+               new_of_old=new_of_old)
+    return out
+
+
+def random_numbering(w, seed=0):
+    """Random vertex and cell numbering: what an unstructured mesh generator without any locality would hand over."""
+    rng = np.random.default_rng(seed)
+    nv, nc = w["mesh"].num_vertices(), w["mesh"].num_cells()
+    out = renumber(w, rng.permutation(nv), rng.permutation(nc))
+    out["name"] = w["name"] + " [random vertex/cell numbering, seed %d]" % seed
+    return out
+
+
+def _spread_bits(x, dim):
+    x = x.astype(np.uint64)
+    if dim == 3:        # 21 bits -> every third bit
+        x = (x | (x << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+        x = (x | (x << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x1249249249249249)
+    else:               # 32 bits -> every second bit
+        x = (x | (x << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x3333333333333333)
+        x = (x | (x << np.uint64(1))) & np.uint64(0x5555555555555555)
+    return x
+
+
+def morton_keys(coords):
+    d = coords.shape[1]
+    lo = coords.min(axis=0)
+    span = float((coords.max(axis=0) - lo).max()) or 1.0
+    bits = 21 if d == 3 else 31
+    q = np.minimum(((coords - lo) / span * (2 ** bits - 1)).astype(np.uint64), np.uint64(2 ** bits - 1))
+    key = np.zeros(len(coords), dtype=np.uint64)
+    for k in range(d):
+        key |= _spread_bits(q[:, k], d) << np.uint64(k)
+    return key
+
+
+def locality_numbering(w, window=1024):
+    """The library's internal reorder for meshes that arrive without locality: vertices along a Morton (Z-order) curve of
+    their coordinates, then -- inside windows of ``window`` consecutive vertices -- by descending vertex degree, so that
+    the 32 rows of a SELL slice have similar lengths (SELL-C-sigma by renumbering); cells sorted by their smallest vertex.
+    Returns the renumbered workload (``new_of_old`` holds the vertex permutation: it is what the dof-permutation API
+    reports)."""
+    mesh = w["mesh"]
+    nv = mesh.num_vertices()
+    order = np.argsort(morton_keys(mesh.coords), kind="stable")            # old id of new position
+    if window > 1:
+        deg = np.bincount(mesh.cells.ravel(), minlength=nv)                 # incident cells ~ row length
+        pos = np.arange(nv)
+        key = (pos // window).astype(np.int64) * (int(deg.max()) + 1) + (int(deg.max()) - deg[order])
+        order = order[np.argsort(key, kind="stable")]
+    new_of_old = np.empty(nv, dtype=np.int64)
+    new_of_old[order] = np.arange(nv)
+    cmin = new_of_old[mesh.cells].min(axis=1)
+    out = renumber(w, new_of_old, np.argsort(cmin, kind="stable"))
+    out["name"] = w["name"] + " [Morton + degree-windowed renumbering]"
+    return out
+
+
 def build_engine(w, device=0):
     from .engine import Engine
     eng = Engine(w["mesh"].coords, w["mesh"].cells, w["cell_mat"], device=device)

@@ -51,9 +51,13 @@ enum { GLIMS_PC_JACOBI = 0,          /* (block-)Jacobi on every block */
 enum { GLIMS_ASMK_ATOMIC = 0,        /* element-parallel, scatter map + RED.ADD.F64 */
        GLIMS_ASMK_GATHER = 1,        /* row-parallel gather through the transposed scatter map: no atomics, deterministic */
        GLIMS_ASMK_SLICE = 2,         /* gather with the element geometry of each 32-row slice staged in shared memory */
-       GLIMS_ASMK_TILE = 3           /* fused residual+Jacobian, one CTA per 16-row tile: vertices, element gradients and
+       GLIMS_ASMK_TILE = 3,          /* fused residual+Jacobian, one CTA per 16-row tile: vertices, element gradients and
                                         contributor lists staged in shared memory, material-free raw sums per slot, residual
-                                        from the same sums; no atomics, deterministic (csrc/tile.h, tile.cu) */ };
+                                        from the same sums; no atomics, deterministic (csrc/tile.h, tile.cu) */
+       GLIMS_ASMK_ROWS = 4           /* default of glims_step: the per-Newton-iteration pass without atomics or scatter map.
+                                        K_uu/K_uc (state independent, stg:110-114) come from the tile kernel once; per iteration
+                                        one row-walk kernel forms K_cc and F_c from per-slot constants + (row, element) pair lists,
+                                        and F_u = K_uu u + K_uc c is one SpMV over the stored blocks (csrc/ccrow.cu) */ };
 
 typedef struct {
     /* SNES-like controls; defaults mirror DOLFIN's PETScSNESSolver defaults that
@@ -117,6 +121,15 @@ int glims_set_dirichlet(glims_ctx* c, int64_t n, const int64_t* dofs, const doub
    pre-integrated into one load vector f_ext[ndof]; F = F_int(x) - f_ext.  NULL clears it. */
 int glims_set_load(glims_ctx* c, const double* f_ext);
 
+/* Dof numbering of the caller.  perm[i] = vertex-blocked index (see top) of the caller's dof i, e.g. built from
+   DOLFIN's vertex_to_dof_map(V) / dofmap().dofs() (helper_classes.py:271-282, data_io.py:242-252) so that
+   `sim.solution.vector()` arrays travel unchanged.  Applies to every ndof-sized HOST vector of this API (state, prev,
+   load, residual) and to the dof indices of glims_set_dirichlet; NULL restores the identity.  Must be called before
+   glims_set_dirichlet.  The reference's own numbering comes from DOLFIN/SCOTCH and cannot be generated offline
+   (DESIGN.md section 3): this entry point is where it is plugged in. */
+int glims_set_dof_permutation(glims_ctx* c, const int64_t* perm);
+int glims_get_dof_permutation(glims_ctx* c, int64_t* perm);          /* ndof entries */
+
 /* ---- state ------------------------------------------------------------------------------- */
 int glims_set_state(glims_ctx* c, const double* x);      /* current Newton iterate / solution  */
 int glims_get_state(glims_ctx* c, double* x);
@@ -135,6 +148,15 @@ void* glims_stream(glims_ctx* c);                        /* cudaStream_t the lib
    Returns GLIMS_ERR_NOT_CONVERGED at the first failing step (state left at the last good step). */
 int glims_step(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, glims_step_stats* stats);
 
+/* One-time work of the first step, callable on its own so that it can be timed (bench.py `setup_s`): K_uu / K_uc assembly
+   and Dirichlet elimination (DOLFIN assembles these inside every solve, stg:124), the AMG hierarchy, the row-walk maps.
+   o == NULL: defaults. */
+int glims_prepare(glims_ctx* c, const glims_solver_opts* o);
+/* Forget what the solver learnt from earlier steps (successive-right-hand-side projection basis, extrapolation history,
+   cached residual norm) without touching matrices, hierarchy or captured graphs: a run restarted from the same initial
+   state then repeats the same iteration counts. */
+int glims_reset_history(glims_ctx* c);
+
 /* ---- building blocks (parity tests, roofline benches) -------------------------------------- */
 
 /* Assemble on the device from the current state / prev; raw = before Dirichlet elimination.
@@ -151,7 +173,8 @@ int glims_spmv(glims_ctx* c, int32_t which, const double* x, double* y);
    one kernel on resident data: kernel 0 = full assembly (residual+Jacobian, `variant` = GLIMS_ASMK_*),
    1 = monolithic SpMV, 2 = K_uu SpMV, 3 = K_cc SpMV, 4 = residual only, 5 = residual + K_cc (the per-Newton-iteration
    pass of the block-triangular solver), 6 = one fused Chebyshev smoother step of the V-cycle's fine level (FP16 matrix,
-   FP32 vectors; needs a step with GLIMS_PC_AMG first). flush_l2 != 0 writes a
+   FP32 vectors; needs a step with GLIMS_PC_AMG first), 7 = the row-walk K_cc + F_c kernel alone (what glims_step launches
+   per Newton iteration), 8 = F_u = K_uu u + K_uc c by SpMV alone. flush_l2 != 0 writes a
    >L2-sized buffer between launches (outside the timed events). */
 int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t reps, int32_t flush_l2,
                       float* ms_avg);

@@ -58,7 +58,7 @@ def relerr(a, b):
 
 
 @pytest.mark.parametrize("d", [2, 3])
-@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3, 4])
 def test_assembly_matches_oracle(d, kernel):
     """K1/K2: residual and Jacobian values, raw and with DOLFIN-style Dirichlet rows; <= 1e-13 relative."""
     prob, rng = small_problem(d)
@@ -94,7 +94,7 @@ def test_atomic_and_gather_kernels_agree(d):
     eng.set_state(rng.standard_normal(prob.ndof))
     eng.assemble(what=6, kernel=0)
     a = eng.export_blocks()
-    for kernel in (1, 2, 3):
+    for kernel in (1, 2, 3, 4):
         eng.assemble(what=6, kernel=kernel)
         b = eng.export_blocks()
         for p, q in zip(a[2:], b[2:]):
@@ -140,6 +140,143 @@ def test_tile_kernel_all_masks_and_configs(d, n, nt, chunk):
     assert np.array_equal(eng.residual(), Fa)
     for p, q in zip(Ka[2:], eng.export_blocks()[2:]):
         assert np.array_equal(p, q)
+    eng.close()
+
+
+@pytest.mark.parametrize("d,n", [(2, 40), (3, 12)])
+def test_rows_kernel_masks_determinism_and_numbering(d, n):
+    """Row-walk assembly (GLIMS_ASMK_ROWS, the default of glims_step): F_c / K_cc from per-slot constants + (row, element)
+    pair lists, F_u by SpMV over the stored K_uu / K_uc.  Every `what` mask leaves exactly the requested outputs equal to
+    the oracle (<= 1e-13), results are bitwise repeatable, a change of dt or of the materials refreshes the constants, and a
+    random vertex / cell numbering (ragged rows, scattered columns) gives the same answer."""
+    prob, rng = small_problem(d, seed=17, n=n, with_bc=False)
+    x, xp = 0.1 * rng.standard_normal(prob.ndof), 0.1 * rng.standard_normal(prob.ndof)
+    eng = make_engine(prob)
+    eng.set_state(x)
+    eng.set_prev(xp)
+    F0, J0 = fem.assemble(prob, x, xp)
+    eng.assemble(what=7, kernel=4)
+    assert relerr(eng.residual(), F0) < 1e-13
+    assert abs(eng.export_jacobian() - J0).max() / abs(J0).max() < 1e-13
+    x2 = 0.1 * rng.standard_normal(prob.ndof)
+    eng.set_state(x2)
+    F2, J2 = fem.assemble(prob, x2, xp)
+    eng.assemble(what=1, kernel=4)                       # residual only: K_cc untouched
+    assert relerr(eng.residual(), F2) < 1e-13
+    assert abs(eng.export_jacobian() - J0).max() / abs(J0).max() < 1e-13
+    Fa = eng.residual().copy()
+    eng.assemble(what=4, kernel=4)                       # K_cc only: F untouched
+    assert np.array_equal(Fa, eng.residual())
+    assert abs(eng.export_jacobian() - J2).max() / abs(J2).max() < 1e-13
+    eng.assemble(what=5, kernel=4)
+    Ka = eng.export_blocks()
+    Fa = eng.residual().copy()
+    eng.assemble(what=5, kernel=4)                       # bitwise repeatable
+    assert np.array_equal(eng.residual(), Fa)
+    for p, q in zip(Ka[2:], eng.export_blocks()[2:]):
+        assert np.array_equal(p, q)
+    # new dt and new materials: the per-slot constants (Klin, M, rho|K|) follow
+    prob.dt = 0.31
+    eng.set_dt(prob.dt)
+    F3, J3 = fem.assemble(prob, x2, xp)
+    eng.assemble(what=7, kernel=4)
+    assert relerr(eng.residual(), F3) < 1e-13
+    assert abs(eng.export_jacobian() - J3).max() / abs(J3).max() < 1e-13
+    prob.mats = fem.Materials.from_E_nu([1e-3, 2e-3, 5e-3], [0.4, 0.2, 0.3], [0.03, 0.0, 0.2], [0.0, 0.3, 0.1], [0.1, 0.2, 0.0])
+    eng.set_materials(prob.mats.table())
+    F4, J4 = fem.assemble(prob, x2, xp)
+    eng.assemble(what=7, kernel=4)
+    assert relerr(eng.residual(), F4) < 1e-13
+    assert abs(eng.export_jacobian() - J4).max() / abs(J4).max() < 1e-13
+    eng.close()
+    # random numbering
+    nv, nb = len(prob.coords), d + 1
+    perm = rng.permutation(nv)
+    inv = np.empty(nv, np.int64)
+    inv[perm] = np.arange(nv)
+    cperm = rng.permutation(len(prob.cells))
+    p2 = fem.Problem(np.ascontiguousarray(prob.coords[perm]), np.ascontiguousarray(inv[prob.cells][cperm].astype(np.int32)),
+                     np.ascontiguousarray(prob.cell_mat[cperm]), prob.mats, prob.dt)
+    p2.f_ext = prob.f_ext.reshape(nv, nb)[perm].ravel()
+    x, xp = 0.1 * rng.standard_normal(p2.ndof), 0.1 * rng.standard_normal(p2.ndof)
+    eng = make_engine(p2)
+    eng.set_state(x)
+    eng.set_prev(xp)
+    F0, J0 = fem.assemble(p2, x, xp)
+    eng.assemble(what=7, kernel=4)
+    assert relerr(eng.residual(), F0) < 1e-13
+    assert abs(eng.export_jacobian() - J0).max() / abs(J0).max() < 1e-13
+    eng.close()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_time_dependent_dirichlet_values_keep_the_hierarchy(d):
+    """Dirichlet VALUES that change from step to step on an unchanged dof set (the reference's time_update_bcs,
+    simulation_base.py:277-300): the library re-uploads the values and rebuilds only the lift of the eliminated columns
+    (K_uu, the AMG hierarchy and the captured graphs stay), and every step still matches the oracle <= 1e-8."""
+    prob, rng = small_problem(d, seed=23, n=8 if d == 3 else 20, jitter=0.2)
+    prob.f_ext = None
+    nb = d + 1
+    x0 = np.zeros(prob.ndof)
+    x0[nb - 1::nb] = np.exp(-8 * ((prob.coords - prob.coords.mean(axis=0)) ** 2).sum(axis=1))
+    base_vals = prob.bc_vals.copy()
+    eng = make_engine(prob)
+    eng.set_load(None)
+    eng.set_prev(x0)
+    eng.set_state(np.zeros(prob.ndof))
+    x_prev, x_start = x0.copy(), np.zeros(prob.ndof)
+    for k in range(1, 4):
+        is_u = (prob.bc_dofs % nb) < d
+        prob.bc_vals = np.where(is_u, base_vals * (1.0 + 0.5 * k), base_vals)    # u data grows in time, c data fixed
+        eng.set_dirichlet(prob.bc_dofs, prob.bc_vals)
+        l0 = eng.launch_count
+        st = eng.step(1, snes_rtol=1e-11, snes_atol=1e-14, ksp_rtol=1e-12)[0]
+        assert st["converged"] == 1
+        x_ref, _ = osolver.newton(prob, x_start.copy(), x_prev, linear="lu", rtol=1e-12, atol=1e-15)
+        x = eng.get_state().reshape(-1, nb)
+        ref = x_ref.reshape(-1, nb)
+        assert np.linalg.norm(x[:, d] - ref[:, d]) / np.linalg.norm(ref[:, d]) < 1e-8, k
+        assert np.linalg.norm(x[:, :d] - ref[:, :d]) / np.linalg.norm(ref[:, :d]) < 1e-8, k
+        x_prev, x_start = x_ref.copy(), x_ref.copy()
+        eng.set_prev(x_ref)
+        eng.set_state(x_ref)
+    eng.close()
+
+
+@pytest.mark.parametrize("config", ["c1", "c3_small"])
+def test_default_tolerances_meet_the_parity_bar(config):
+    """The tolerances bench.py times (glims_default_opts: SNES rtol 1e-9 / atol 1e-10, KSP rtol 1e-10) against the oracle
+    solved to 1e-12: <= 1e-8 relative L2 per field and step (the timed configuration must be the
+    parity-tested one)."""
+    if config == "c1":
+        prob, x0 = c1_problem()
+        nb, steps = 3, 10
+    else:
+        coords, cells = meshes.box_mesh((0, 0, 0), (1, 1, 1), 10, 10, 10)
+        cm = (coords[cells].mean(axis=1)[:, 0] >= 0.5).astype(np.int32)
+        mats = fem.Materials.from_E_nu([3e-3, 1e-3], [0.45, 0.45], [2e-4, 0.0], [0.05, 0.0], [0.1, 0.0])
+        bv = meshes.boundary_vertices(cells, len(coords))
+        dofs = np.sort((bv[:, None] * 4 + np.arange(3)[None, :]).ravel())
+        prob = fem.Problem(coords, cells, cm, mats, dt=1.0, bc_dofs=dofs, bc_vals=np.zeros(len(dofs)))
+        x0 = np.zeros(prob.ndof)
+        x0[3::4] = np.exp(-60.0 * ((coords - np.array([0.3, 0.5, 0.5])) ** 2).sum(axis=1))
+        nb, steps = 4, 5
+    d = nb - 1
+    recs, _ = osolver.run(prob, x0, steps, linear="lu", rtol=1e-12, atol=1e-15)
+    eng = make_engine(prob)
+    eng.set_prev(x0)
+    eng.set_state(np.zeros(prob.ndof))
+    worst = 0.0
+    for k in range(1, steps + 1):
+        st = eng.step(1)[0]                      # library defaults
+        assert st["converged"] == 1
+        x = eng.get_state().reshape(-1, nb)
+        ref = recs[k][2].reshape(-1, nb)
+        ec = np.linalg.norm(x[:, d] - ref[:, d]) / np.linalg.norm(ref[:, d])
+        eu = np.linalg.norm(x[:, :d] - ref[:, :d]) / np.linalg.norm(ref[:, :d])
+        worst = max(worst, ec, eu)
+        assert ec < 1e-8 and eu < 1e-8, (config, k, ec, eu)
+    print("default tolerances, %s: worst relative L2 error over %d steps %.2e" % (config, steps, worst))
     eng.close()
 
 
