@@ -53,6 +53,36 @@ class Mesh(_mesh.SimplexMesh):
         self.__dict__.update(_mesh.SimplexMesh(other.coords, other.cells).__dict__)
 
 
+class MeshEditor:
+    """``fenics.MeshEditor``: build a mesh vertex by vertex / cell by cell (data_io.py:458-468, 495-505)."""
+
+    def open(self, mesh, cell_type, tdim, gdim, degree=1):
+        if isinstance(cell_type, int):          # 2017.2 also accepts (mesh, tdim, gdim)
+            cell_type, tdim, gdim = ("triangle" if cell_type == 2 else "tetrahedron"), cell_type, tdim
+        self._mesh, self._tdim, self._gdim = mesh, int(tdim), int(gdim)
+        if cell_type not in ("triangle", "tetrahedron"):
+            raise ValueError("MeshEditor: only simplex cells are supported")
+
+    def init_vertices(self, n):
+        self._pts = np.zeros((int(n), self._gdim))
+
+    init_vertices_global = init_vertices
+
+    def init_cells(self, n):
+        self._cells = np.zeros((int(n), self._tdim + 1), dtype=np.int32)
+
+    init_cells_global = init_cells
+
+    def add_vertex(self, i, x):
+        self._pts[int(i)] = np.asarray(x.array() if hasattr(x, "array") else x, dtype=np.float64)[:self._gdim]
+
+    def add_cell(self, i, verts):
+        self._cells[int(i)] = np.asarray(verts, dtype=np.int64)
+
+    def close(self, order=True):
+        self._mesh._assign(_mesh.SimplexMesh(self._pts, self._cells))
+
+
 def _as_mesh(sm):
     m = Mesh(sm.coords, sm.cells)
     if getattr(sm, "_boundary_vertices", None) is not None:

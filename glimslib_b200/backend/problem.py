@@ -24,12 +24,40 @@ class CoupledRDMechanicsForm:
     """
 
     def __init__(self, function_space, solution, u_previous, cell_mat, table, dt, body_force=None,
-                 source=None, neumann=(), engine_cache=None):
+                 source=None, neumann=(), engine_cache=None, table_fn=None):
         self.V, self.solution, self.u_previous = function_space, solution, u_previous
         self.cell_mat = np.ascontiguousarray(cell_mat, dtype=np.int32)
         self.table = np.ascontiguousarray(table, dtype=np.float64)
         self.dt, self.body_force, self.source, self.neumann = float(dt), body_force, source, list(neumann)
         self.engine_cache = engine_cache if engine_cache is not None else {}
+        self.table_fn = table_fn          # re-evaluates the per-label coefficients (time-dependent parameters)
+
+    @staticmethod
+    def _coef_sig(obj):
+        """What a coefficient object currently evaluates to, cheaply: its time stamp `.t` (set by
+        simulation_base._update_expressions every step), its user parameters and, for Constants, its values."""
+        if obj is None:
+            return None
+        sig = [id(obj)]
+        if isinstance(obj, core.Constant):
+            sig.append(obj.values().tobytes())          # a `.t` stamped on a Constant changes nothing
+        elif isinstance(obj, core.Expression):
+            sig.append(repr(sorted((k, repr(v)) for k, v in obj.__dict__.get("_params", {}).items())))
+            sig.append(repr(obj.__dict__.get("t")))     # Python subclasses whose eval() reads self.t
+        elif isinstance(obj, (int, float)):
+            sig.append(float(obj))
+        else:
+            try:
+                sig.append(("t", float(obj.t)))
+            except Exception:
+                pass
+        return tuple(sig)
+
+    def coefficient_signature(self):
+        """Changes whenever a load term (body force, source, von-Neumann value) may evaluate differently than at the last
+        solve -- the reference's UFL form re-evaluates them at every assembly (stg:110-120)."""
+        return (self._coef_sig(self.body_force), self._coef_sig(self.source),
+                tuple(self._coef_sig(v) for _, _, v in self.neumann))
 
     def load_vector(self):
         """f_ext so that F = F_int - f_ext: body force (stg:112), RD source (stg:119), Neumann terms (stg:113,120)."""
@@ -112,7 +140,7 @@ class NonlinearVariationalSolver:
                                                maximum_iterations=20000))
         self.parameters = _Params(nonlinear_solver="newton", snes_solver=snes, newton_solver=newton,
                                   # B200 backend extensions
-                                  b200=_Params(solver="block_tri", preconditioner="amg", assembly="atomic",
+                                  b200=_Params(solver="block_tri", preconditioner="amg", assembly="rows",
                                                lag_mechanics=True, device=0))
         self._engine = None
         self._pushed_version = (None, None)
@@ -137,7 +165,26 @@ class NonlinearVariationalSolver:
         eng.set_materials(form.table)
         eng.set_dt(form.dt)
         eng.set_load(form.load_vector())
+        self._coef_sig = form.coefficient_signature()
+        self._table_pushed = form.table.copy()
         self._configured = True
+
+    def _refresh_coefficients(self, eng):
+        """Time-dependent coefficients: simulation_base._update_expressions(t) stamps `.t` on parameters and boundary
+        values before every solve and the reference's form picks the new values up at assembly time.  Here the material
+        table and the pre-integrated load vector live on the device, so they are re-pushed when (and only when) something
+        they were built from changed."""
+        form = self.problem.form
+        if form.table_fn is not None:
+            table = np.ascontiguousarray(form.table_fn(), dtype=np.float64)
+            if table.shape != self._table_pushed.shape or not np.array_equal(table, self._table_pushed):
+                form.table = table
+                eng.set_materials(table)
+                self._table_pushed = table.copy()
+        sig = form.coefficient_signature()
+        if sig != self._coef_sig:
+            eng.set_load(form.load_vector())
+            self._coef_sig = sig
 
     def _bc_arrays(self):
         dofs, vals = [], []
@@ -162,6 +209,7 @@ class NonlinearVariationalSolver:
             self._configure(self._engine)
             self._bc_sig = None
         eng = self._engine
+        self._refresh_coefficients(eng)
         dofs, vals = self._bc_arrays()
         sig = (hash(dofs.tobytes()), hash(vals.tobytes()))
         if sig != self._bc_sig:
@@ -176,7 +224,7 @@ class NonlinearVariationalSolver:
                     max_krylov=int(ks.maximum_iterations),
                     solver=N.SOLVER_MONO_GMRES if prm.b200.solver == "mono_gmres" else N.SOLVER_BLOCK_TRI,
                     pc=N.PC_AMG if prm.b200.preconditioner == "amg" else N.PC_JACOBI,
-                    asm_kernel=N.ASMK_GATHER if prm.b200.assembly == "gather" else N.ASMK_ATOMIC,
+                    asm_kernel={"gather": N.ASMK_GATHER, "atomic": N.ASMK_ATOMIC, "tile": N.ASMK_TILE}.get(prm.b200.assembly, N.ASMK_ROWS),
                     lag_mechanics=int(bool(prm.b200.lag_mechanics)))
         u, up = self.problem.u, form.u_previous
         # host -> device only for what changed on the host since the last solve

@@ -36,6 +36,8 @@ struct CcMap {
     int* pl_w = nullptr;        // [n_slices] list iterations of the slice (longest row)
     unsigned* pe = nullptr;     // [total] element | own local vertex << 30 ; 0xFFFFFFFF = padding
     unsigned* pp = nullptr;     // [total] column (inside the row) of the element's local vertex q in byte q
+    double* prv = nullptr;      // [total] rho_e |K_e| of the entry's element (0 for padding): what k_cc_rows streams
+    unsigned* ppa = nullptr;    // [total] four 7-bit columns | own local vertex << 28 (0 for padding)
     i64 total = 0;
     int max_pw = 0;
     double* rvol = nullptr;     // [n_c] rho_e |K_e|
@@ -51,7 +53,7 @@ namespace {
 
 constexpr int CC_TPB = 128;                 // 4 warps = 4 slices per CTA
 constexpr unsigned CC_PAD = 0xFFFFFFFFu;
-constexpr int CC_MAX_W = 96;                // widest row (block columns) the shared-memory strips are sized for
+constexpr int CC_MAX_W = 96;                // widest row (block columns): 7-bit columns in the stream, shared-memory strips
 inline int nblk(i64 n, int t = 256) { return (int)((n + t - 1) / t); }
 
 __global__ void k_pair_keys(const int* __restrict__ cells, i64 n_c, int nb, i64 n_own, unsigned long long* keys) {
@@ -73,7 +75,7 @@ __global__ void k_pair_width(const i64* __restrict__ pstart, int n_rows, int n_s
         int r = S * 32 + l;
         if (r < n_rows) m = max(m, (int)(pstart[r + 1] - pstart[r]));
     }
-    w[S] = m;
+    w[S] = (m + 3) & ~3;      // k_cc_rows walks the list four iterations at a time
 }
 __global__ void k_times32(i64* v, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,58 +198,88 @@ k_mass_cprev(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
     if (r < n_rows) mcp[r] = acc;
 }
 
-// The per-Newton-iteration pass: K_cc (WK) and F_c from the current concentration.
+// (rho|K|, columns) stream of the main kernel from the element ids (after every change of the materials)
+__global__ void k_pair_stream(const unsigned* __restrict__ pe, const unsigned* __restrict__ pp, i64 n,
+                              const double* __restrict__ rvol, double* __restrict__ prv, unsigned* __restrict__ ppa) {
+    i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const unsigned ea = pe[t];
+    if (ea == CC_PAD) { prv[t] = 0.0; ppa[t] = 0u; return; }
+    const unsigned ps = pp[t];
+    prv[t] = rvol[ea & 0x3FFFFFFFu];
+    ppa[t] = (ps & 127u) | (((ps >> 8) & 127u) << 7) | (((ps >> 16) & 127u) << 14) | (((ps >> 24) & 127u) << 21) | ((ea >> 30) << 28);
+}
+
+// The per-Newton-iteration pass: K_cc (WK) and F_c from the current concentration.  Branch-free: padding entries carry
+// rho|K| = 0 and column 0, i.e. they add 0.0; the list is streamed four iterations ahead of the shared-memory updates.
 template <int D, bool WK>
 __global__ void __launch_bounds__(CC_TPB)
 k_cc_rows(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col, int n_rows,
-          int n_slices, const i64* __restrict__ pl_off, const int* __restrict__ pl_w, const unsigned* __restrict__ pe,
-          const unsigned* __restrict__ pp, const double* __restrict__ rvol, const double* __restrict__ Klin,
+          int n_slices, const i64* __restrict__ pl_off, const int* __restrict__ pl_w, const double* __restrict__ prv,
+          const unsigned* __restrict__ ppa, const double* __restrict__ Klin,
           const double* __restrict__ mcp, const double* __restrict__ fext, const double* __restrict__ x, double dt,
           int max_w, double* __restrict__ Kcc, double* __restrict__ F) {
     constexpr int NB = D + 1;
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* cc = sm + (size_t)warp * 2 * max_w * 32;     // c of the row's columns
-    double* acc = cc + max_w * 32;                       // A(a, column)
+    double* __restrict__ cc = sm + (size_t)warp * 2 * max_w * 32 + lane;     // c of the row's columns   [column*32]
+    double* __restrict__ acc = cc + max_w * 32;                              // A(a, column)             [column*32]
     const int S = blockIdx.x * (CC_TPB / 32) + warp;
     if (S >= n_slices) return;
-    const i64 base = slice_off[S];
+    const i64 base = slice_off[S] + lane;
     const int w = slice_w[S];
+#pragma unroll 4
     for (int j = 0; j < w; ++j) {
-        const int cidx = __ldg(&col[base + (i64)j * 32 + lane]);
-        cc[j * 32 + lane] = __ldg(&x[(i64)cidx * NB + D]);
-        acc[j * 32 + lane] = 0.0;
+        const int cidx = __ldg(&col[base + (i64)j * 32]);
+        cc[j * 32] = __ldg(&x[(i64)cidx * NB + D]);
+        acc[j * 32] = 0.0;
     }
-    const i64 po = pl_off[S];
-    const int pw = pl_w[S];
-    for (int t = 0; t < pw; ++t) {
-        const unsigned ea = __ldcs(&pe[po + (i64)t * 32 + lane]);
-        const unsigned ps = __ldcs(&pp[po + (i64)t * 32 + lane]);
-        if (ea == CC_PAD) continue;
-        const double rv = __ldg(&rvol[ea & 0x3FFFFFFFu]);
-        if (rv == 0.0) continue;                         // tissue without proliferation: nothing state dependent
-        const int a = (int)(ea >> 30);
-        int p[NB];
-        double cq[NB], Ssum = 0.0, ca = 0.0;
+    const double* __restrict__ lrv = prv + pl_off[S] + lane;
+    const unsigned* __restrict__ lpa = ppa + pl_off[S] + lane;
+    const int pw = pl_w[S];            // multiple of 4
+    double rv[4];
+    unsigned ps[4];
+    if (pw > 0) {
 #pragma unroll
-        for (int q = 0; q < NB; ++q) {
-            p[q] = (int)((ps >> (8 * q)) & 255u) * 32 + lane;
-            cq[q] = cc[p[q]];
-            Ssum += cq[q];
-            if (q == a) ca = cq[q];
+        for (int u = 0; u < 4; ++u) { rv[u] = __ldcs(&lrv[u * 32]); ps[u] = __ldcs(&lpa[u * 32]); }
+    }
+    for (int t = 0; t < pw; t += 4) {
+        double rvn[4] = {0.0, 0.0, 0.0, 0.0};
+        unsigned psn[4] = {0u, 0u, 0u, 0u};
+        if (t + 4 < pw) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { rvn[u] = __ldcs(&lrv[(t + 4 + u) * 32]); psn[u] = __ldcs(&lpa[(t + 4 + u) * 32]); }
         }
 #pragma unroll
-        for (int q = 0; q < NB; ++q)
-            acc[p[q]] += rv * (q == a ? 4.0 * ca + 2.0 * Ssum : ca + cq[q] + Ssum);
+        for (int u = 0; u < 4; ++u) {
+            const int a = (int)(ps[u] >> 28);
+            int p[NB];
+            double cq[NB], av[NB], Ssum = 0.0, ca = 0.0;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                p[q] = (int)((ps[u] >> (7 * q)) & 127u) * 32;
+                cq[q] = cc[p[q]];
+                av[q] = acc[p[q]];
+                Ssum += cq[q];
+                if (q == a) ca = cq[q];
+            }
+            // the NB columns of a real entry are distinct; a padding entry hits column 0 NB times with +0.0
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+                acc[p[q]] = av[q] + rv[u] * (q == a ? 4.0 * ca + 2.0 * Ssum : ca + cq[q] + Ssum);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { rv[u] = rvn[u]; ps[u] = psn[u]; }
     }
     const double kf = 2.0 * dt * Consts<D>::kappa;
     double fc = 0.0;
+#pragma unroll 4
     for (int j = 0; j < w; ++j) {
-        const i64 s = base + (i64)j * 32 + lane;
+        const i64 s = base + (i64)j * 32;
         const double kl = __ldcs(&Klin[s]);
-        const double jr = kf * acc[j * 32 + lane];
+        const double jr = kf * acc[j * 32];
         if (WK) __stcs(&Kcc[s], kl + jr);
-        fc += (kl + 0.5 * jr) * cc[j * 32 + lane];
+        fc += (kl + 0.5 * jr) * cc[j * 32];
     }
     const int r = S * 32 + lane;
     if (F && r < n_rows) F[(i64)r * NB + D] = fc - mcp[r] - (fext ? fext[(i64)r * NB + D] : 0.0);
@@ -316,7 +348,7 @@ T* dalloc(i64 n, size_t& bytes) {
 void cc_free(glims_ctx* c) {
     CcMap* m = (CcMap*)c->ccmap;
     if (!m) return;
-    for (void* q : {(void*)m->pl_off, (void*)m->pl_w, (void*)m->pe, (void*)m->pp, (void*)m->rvol, (void*)m->Klin,
+    for (void* q : {(void*)m->pl_off, (void*)m->pl_w, (void*)m->pe, (void*)m->pp, (void*)m->prv, (void*)m->ppa, (void*)m->rvol, (void*)m->Klin,
                     (void*)m->Mass, (void*)m->mcp, (void*)m->lift})
         if (q) cudaFree(q);
     delete m;
@@ -361,6 +393,8 @@ static CcMap* cc_ensure(glims_ctx* c) {
     GL_CUDA(cudaMemsetAsync(m->pp, 0, sizeof(unsigned) * std::max<i64>(m->total, 1), c->stream));
     k_pair_fill<<<nblk(nvalid), 256, 0, c->stream>>>(kp, nvalid, nb, thrust::raw_pointer_cast(pstart.data()), m->pl_off,
                                                      p.slice_off, c->eslot, m->pe, m->pp);
+    m->prv = dalloc<double>(m->total, m->map_bytes);
+    m->ppa = dalloc<unsigned>(m->total, m->map_bytes);
     m->rvol = dalloc<double>(c->n_c, m->map_bytes);
     m->Klin = dalloc<double>(p.n_slots, m->map_bytes);
     m->Mass = dalloc<double>(p.n_slots, m->map_bytes);
@@ -388,7 +422,8 @@ static void cc_consts_dim(glims_ctx* c, CcMap* m) {
     k_rvol<D><<<nblk(c->n_c), 256, 0, c->stream>>>(c->coords, c->cells, c->cell_mat, c->mat, c->n_c, m->rvol);
     kfn<<<nblk(p.n_slices, CC_TPB / 32), CC_TPB, smem, c->stream>>>(p.slice_off, p.slice_w, p.n_slices, m->pl_off, m->pl_w,
         m->pe, m->pp, c->coords, c->cells, c->cell_mat, c->mat, c->dt, std::max(p.max_w, 1), m->Klin, m->Mass);
-    c->launches += 2;
+    k_pair_stream<<<nblk(m->total), 256, 0, c->stream>>>(m->pe, m->pp, m->total, m->rvol, m->prv, m->ppa);
+    c->launches += 3;
 }
 static void cc_ensure_consts(glims_ctx* c, CcMap* m) {
     if (m->const_valid) return;
@@ -417,8 +452,8 @@ static void cc_rows_dim(glims_ctx* c, CcMap* m, bool with_kcc, bool with_res) {
     const double* fext = c->have_load ? c->fext : nullptr;
 #define CC_GO(WK) do { auto kfn = k_cc_rows<D, WK>; \
         GL_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kfn<<<g, CC_TPB, smem, c->stream>>>(p.slice_off, p.slice_w, p.col, p.n_rows, p.n_slices, m->pl_off, m->pl_w, m->pe, \
-            m->pp, m->rvol, m->Klin, m->mcp, fext, c->x, c->dt, std::max(p.max_w, 1), c->Kcc, with_res ? c->F : nullptr); } while (0)
+        kfn<<<g, CC_TPB, smem, c->stream>>>(p.slice_off, p.slice_w, p.col, p.n_rows, p.n_slices, m->pl_off, m->pl_w, m->prv, \
+            m->ppa, m->Klin, m->mcp, fext, c->x, c->dt, std::max(p.max_w, 1), c->Kcc, with_res ? c->F : nullptr); } while (0)
     if (with_kcc) CC_GO(true); else CC_GO(false);
 #undef CC_GO
     c->launches++;

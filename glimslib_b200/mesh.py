@@ -7,13 +7,21 @@ triangles per quad, six tetrahedra per hexahedron around the (v0, v7) diagonal. 
 import numpy as np
 
 
+class _Dim(int):
+    """Geometric dimension that is both the int the backend computes with (``mesh.dim``, ``mesh.geometry().dim - 1``)
+    and DOLFIN's method (``mesh.geometry().dim()``, used 16x in the reference, e.g. simulation_base.py:98)."""
+
+    def __call__(self):
+        return int(self)
+
+
 class SimplexMesh:
     """Vertices + cells of a 2D/3D simplex mesh with lazily built facet topology."""
 
     def __init__(self, coords, cells):
         self.coords = np.ascontiguousarray(coords, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
-        self.dim = self.coords.shape[1]
+        self.dim = _Dim(self.coords.shape[1])
         assert self.cells.shape[1] == self.dim + 1
         self._facets = None
 

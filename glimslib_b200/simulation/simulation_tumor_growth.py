@@ -61,7 +61,8 @@ class TumorGrowth(FenicsSimulation):
         neumann = self.bcs.neumann_terms(0) + self.bcs.neumann_terms(1)
         F = fenics.CoupledRDMechanicsForm(W, self.solution, u_previous, cell_mat.reshape(-1), table,
                                           dt=float(self.params.sim_time_step), body_force=self.body_force,
-                                          source=self.source_term, neumann=neumann, engine_cache=self._engine_cache)
+                                          source=self.source_term, neumann=neumann, engine_cache=self._engine_cache,
+                                          table_fn=lambda: self._material_rows(labels))
         problem = fenics.NonlinearVariationalProblem(F, self.solution, bcs=getattr(self.bcs, "dirichlet_bcs", []), J=None)
         solver = fenics.NonlinearVariationalSolver(problem)
         prm = solver.parameters
