@@ -18,6 +18,8 @@
 #include <cmath>
 #include <numeric>
 #include <cstdlib>
+#include <cstring>
+#include <functional>
 
 namespace {
 
@@ -48,6 +50,14 @@ struct Level {
     __half* A16 = nullptr;      // fine level only (optional): matrix values in FP16, scaled by a power of two
     float a16_unscale = 1.f;    // multiply row sums by this to undo the scaling
     float* y32 = nullptr;       // second iterate buffer: the fused smoother steps ping-pong between x32 and y32
+    // Partitioned mesh (one rank per GPU): level 0 is distributed by rows (ghost halo exchange); level 1 is the GLOBAL
+    // Galerkin operator, replicated on every rank, of which a rank applies only the rows of its own aggregates
+    // [row0, row0 + rows) and all-gathers the vector segments; levels >= 2 are small and run redundantly on every rank.
+    bool dist_rows = false;     // level 1 of a distributed hierarchy
+    int row0 = 0, rows = 0;     // own row range (multiples of 32)
+    int nc_off = 0;             // level 0 of a distributed hierarchy: first global id of this rank's aggregates
+    int nc_local = 0;           //   ... and their number (l.nc is the size of the coarse level)
+    void* sym = nullptr;        // dist_rows: symmetric buffer holding x32 | y32 | r32 (comm.cu)
 };
 
 }  // namespace
@@ -61,6 +71,9 @@ struct Amg {
     int cheb_degree = 2;
     int coarse_degree = 2;      // smoother degree on levels >= 1 (GLIMS_AMG_COARSE_DEGREE)
     double cheb_ratio = 0.1;
+    bool dist = false;          // hierarchy of a partitioned mesh (see Level::dist_rows)
+    int n_ranks = 1, rank = 0;
+    void* fused = nullptr;      // FusedPlan: levels >= 2 of the FP32 V-cycle in one persistent kernel (amg_fused.cuh)
 };
 
 namespace {
@@ -103,6 +116,33 @@ __global__ void k_coarse_keys(const i64* __restrict__ slice_off, const int* __re
             if (I >= 0 && J >= 0) key = ((unsigned long long)(unsigned)I << 32) | (unsigned)J;
         }
         keys[base + t] = key;
+    }
+}
+
+// diagonal keys (I, I) for I in [first, first + n): every node of a rank's segment gets a diagonal block, padding included
+__global__ void k_diag_keys(unsigned long long* keys, int first, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((unsigned long long)(unsigned)(first + i) << 32) | (unsigned)(first + i);
+}
+// SELL values <-> CSR-ordered blocks [t][nc]
+__global__ void k_sell_to_csr(const i64* __restrict__ rowptr, const i64* __restrict__ slice_off, int n_rows, int nc,
+                              const double* __restrict__ A, double* __restrict__ out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const i64 base = slice_off[r >> 5];
+    for (i64 t = rowptr[r]; t < rowptr[r + 1]; ++t) {
+        const i64 s = base + (t - rowptr[r]) * 32 + (r & 31);
+        for (int k = 0; k < nc; ++k) out[t * nc + k] = A[vidx(s, k, nc)];
+    }
+}
+__global__ void k_csr_to_sell(const i64* __restrict__ rowptr, const i64* __restrict__ slice_off, int n_rows, int nc,
+                              const double* __restrict__ in, double* __restrict__ A) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const i64 base = slice_off[r >> 5];
+    for (i64 t = rowptr[r]; t < rowptr[r + 1]; ++t) {
+        const i64 s = base + (t - rowptr[r]) * 32 + (r & 31);
+        for (int k = 0; k < nc; ++k) A[vidx(s, k, nc)] = in[t * nc + k];
     }
 }
 
@@ -504,9 +544,9 @@ template <int BS, bool RESID, typename MT>
 __global__ void __launch_bounds__(32 * BS)
 k_spmv32_split(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
                const MT* __restrict__ A, const float* __restrict__ x, float* __restrict__ y, int n_rows,
-               int n_slices, const float* __restrict__ rhs, float unscale) {
+               int slice0, int n_slices, const float* __restrict__ rhs, float unscale) {
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
-    for (int S = blockIdx.x; S < n_slices; S += gridDim.x) {
+    for (int S = slice0 + blockIdx.x; S < slice0 + n_slices; S += gridDim.x) {
         const int r = S * 32 + lane;
         const i64 base = slice_off[S];
         const int w = slice_w[S];
@@ -592,11 +632,11 @@ template <int BS, typename MT>
 __global__ void __launch_bounds__(32 * BS)
 k_spmv32_split_cheb(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
                     const MT* __restrict__ A, const float* __restrict__ x, float* __restrict__ xn, int n_rows,
-                    int n_slices, const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d,
+                    int slice0, int n_slices, const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d,
                     float c1, float c2, float unscale) {
     __shared__ float rs[BS][32];
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
-    for (int S = blockIdx.x; S < n_slices; S += gridDim.x) {
+    for (int S = slice0 + blockIdx.x; S < slice0 + n_slices; S += gridDim.x) {
         const int r = S * 32 + lane;
         const i64 base = slice_off[S];
         const int w = slice_w[S];
@@ -705,9 +745,10 @@ inline int sgrid(i64 n) { i64 g = (n + TPB - 1) / TPB; return (int)(g < 1 ? 1 : 
 void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) {
     const SellPattern& p = l.pat;
     if (l.owns_A) {      // coarse levels (6x6 blocks in 3D, 3x3 in 2D): few rows, use the split kernel
-        int g = p.n_slices < 148 * 16 ? p.n_slices : 148 * 16;
+        const int s0 = l.dist_rows ? l.row0 / 32 : 0, ns = l.dist_rows ? l.rows / 32 : p.n_slices;     // own rows only
+        int g = ns < 148 * 16 ? ns : 148 * 16;
         if (g < 1) g = 1;
-#define SPLIT_GO(BS, RES, MT, AP, US) k_spmv32_split<BS, RES, MT><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, y, p.n_rows, p.n_slices, rhs, US)
+#define SPLIT_GO(BS, RES, MT, AP, US) k_spmv32_split<BS, RES, MT><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, y, p.n_rows, s0, ns, rhs, US)
         if (l.A16) {
             if (l.bs == 6) { if (rhs) SPLIT_GO(6, true, __half, l.A16, l.a16_unscale); else SPLIT_GO(6, false, __half, l.A16, l.a16_unscale); }
             else { if (rhs) SPLIT_GO(3, true, __half, l.A16, l.a16_unscale); else SPLIT_GO(3, false, __half, l.A16, l.a16_unscale); }
@@ -742,9 +783,10 @@ void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) 
 void cheb_step32(glims_ctx* c, Level& l, const float* b, const float* x, float* xn, float c1, float c2) {
     auto& p = l.pat;
     if (l.owns_A) {      // coarse levels: split kernel, like spmv32
-        int g = p.n_slices < 148 * 16 ? p.n_slices : 148 * 16;
+        const int s0 = l.dist_rows ? l.row0 / 32 : 0, ns = l.dist_rows ? l.rows / 32 : p.n_slices;     // own rows only
+        int g = ns < 148 * 16 ? ns : 148 * 16;
         if (g < 1) g = 1;
-#define SPLITC_GO(BS, MT, AP, US) k_spmv32_split_cheb<BS, MT><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, xn, p.n_rows, p.n_slices, b, l.dinv32, l.d32, c1, c2, US)
+#define SPLITC_GO(BS, MT, AP, US) k_spmv32_split_cheb<BS, MT><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, xn, p.n_rows, s0, ns, b, l.dinv32, l.d32, c1, c2, US)
         if (l.A16) { if (l.bs == 6) SPLITC_GO(6, __half, l.A16, l.a16_unscale); else SPLITC_GO(3, __half, l.A16, l.a16_unscale); }
         else { if (l.bs == 6) SPLITC_GO(6, float, l.A32, 1.f); else SPLITC_GO(3, float, l.A32, 1.f); }
 #undef SPLITC_GO
@@ -775,11 +817,20 @@ struct ChebCoef {                 // Chebyshev recurrence for the interval [rati
 // V-cycle in FP32 with fused smoother steps.  The iterate ping-pongs between l.y32 and x; with `degree` pre- and
 // post-smoothing steps there are 2*degree-1 fused steps after the first (zero-guess) one, an odd number, so starting
 // in l.y32 leaves the result in x.
-void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
+#include "amg_fused.cuh"
+
+void vcycle32(glims_ctx* c, Amg* amg, int li, float* b, float* x) {
     Level& l = amg->L[li];
     const int D = amg->dim;
+    // own row range: everything, except on level 1 of a partitioned mesh (Level::dist_rows)
+    const bool dr = l.dist_rows;
+    const i64 o = dr ? (i64)l.row0 * l.bs : 0;                  // first own entry of a level vector
+    const int n_own = dr ? l.rows : l.n;
+    const i64 seg = (i64)n_own * l.bs;
+    auto gather = [&](float* v) { if (dr) allgather_f32(c, l.sym, v, seg); };
     if (li == (int)amg->L.size() - 1) {
         int m = amg->coarse_m;
+        gather(b);
         k_dense_matvec32<<<(m + 7) / 8, 256, 0, c->stream>>>(amg->coarse_inv32, b, x, m);
         c->launches++;
         return;
@@ -792,40 +843,55 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, const float* b, float* x) {
     {   // pre-smoothing from a zero guess
         ChebCoef cc(l.lmax, amg->cheb_ratio);
         cc.step(0, c1, c2);
-        const int g = sgrid(l.n);
-        if (l.bs == 2) k_cheb_first32<2><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, l.n, (float)c2);
-        else if (l.bs == 3) k_cheb_first32<3><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, l.n, (float)c2);
-        else k_cheb_first32<6><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, l.n, (float)c2);
+        const int g = sgrid(n_own);
+        if (l.bs == 2) k_cheb_first32<2><<<g, TPB, 0, c->stream>>>(l.dinv32, b, l.d32, cur, n_own, (float)c2);
+        else if (l.bs == 3) k_cheb_first32<3><<<g, TPB, 0, c->stream>>>(l.dinv32 + o * l.bs, b + o, l.d32 + o, cur + o, n_own, (float)c2);
+        else k_cheb_first32<6><<<g, TPB, 0, c->stream>>>(l.dinv32 + o * l.bs, b + o, l.d32 + o, cur + o, n_own, (float)c2);
         c->launches++;
         for (int k = 1; k < degree; ++k) {
             cc.step(k, c1, c2);
             if (l0) halo_exchange_f32(c, cur, l.bs);
+            gather(cur);
             cheb_step32(c, l, b, cur, oth, (float)c1, (float)c2);
             std::swap(cur, oth);
         }
     }
     if (l0) halo_exchange_f32(c, cur, l.bs);
+    gather(cur);
     spmv32(c, l, cur, l.r32, b);
-    if (l.nc >= 16384) {      // many aggregates: thread per aggregate; few: warp per aggregate (latency)
-        if (D == 2) k_restrict32_serial<2><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
-        else k_restrict32_serial<3><<<nblk(l.nc), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
-    } else if (D == 2) k_restrict32<2><<<nblk(l.nc, TPB / 32), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
-    else k_restrict32<3><<<nblk(l.nc, TPB / 32), TPB, 0, c->stream>>>(l.nc, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, lc.b32);
-    c->launches++;
-    vcycle32(c, amg, li + 1, lc.b32, lc.x32);
-    if (D == 2) k_prolong_add32<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
-    else k_prolong_add32<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
-    c->launches++;
+    gather(l.r32);                    // level 1 of a partitioned mesh: what follows runs redundantly on every rank
+    if (li >= 1 && amg_fused_run(c, amg, li, cur)) {
+        // levels li+1 .. coarsest ran in one persistent kernel: restriction of r32, the coarse V-cycle and the
+        // prolongation into `cur` included (amg_fused.cuh)
+    } else {
+        float* rc = lc.b32 + (i64)l.nc_off * lc.bs;
+        const int nca = l.nc_local;
+        if (nca >= 16384) {      // many aggregates: thread per aggregate; few: warp per aggregate (latency)
+            if (D == 2) k_restrict32_serial<2><<<nblk(nca), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
+            else k_restrict32_serial<3><<<nblk(nca), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
+        } else if (nca > 0) {
+            if (D == 2) k_restrict32<2><<<nblk(nca, TPB / 32), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
+            else k_restrict32<3><<<nblk(nca, TPB / 32), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
+        }
+        c->launches++;
+        vcycle32(c, amg, li + 1, lc.b32, lc.x32);
+        // level 1 of a partitioned mesh: every rank prolongs ALL nodes (its copy of `cur` is complete after the gather
+        // above and x of level 2 is identical everywhere), so the first post-smoothing step needs no exchange
+        if (D == 2) k_prolong_add32<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
+        else k_prolong_add32<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
+        c->launches++;
+    }
     {   // post-smoothing
         ChebCoef cc(l.lmax, amg->cheb_ratio);
         for (int k = 0; k < degree; ++k) {
             cc.step(k, c1, c2);
             if (l0) halo_exchange_f32(c, cur, l.bs);
+            if (k > 0) gather(cur);
             cheb_step32(c, l, b, cur, oth, (float)c1, (float)c2);
             std::swap(cur, oth);
         }
     }
-    if (cur != x) GL_CUDA(cudaMemcpyAsync(x, cur, sizeof(float) * (i64)l.n * l.bs, cudaMemcpyDeviceToDevice, c->stream));
+    if (cur != x) GL_CUDA(cudaMemcpyAsync(x + o, cur + o, sizeof(float) * seg, cudaMemcpyDeviceToDevice, c->stream));
 }
 
 void build_fp32(glims_ctx* c, Amg* amg) {
@@ -853,6 +919,15 @@ void build_fp32(glims_ctx* c, Amg* amg) {
         }
         GL_CUDA(cudaMalloc(&l.dinv32, sizeof(float) * std::max<i64>(nd, 1)));
         k_to_float<<<sgrid(nd), TPB, 0, c->stream>>>(l.dinv, l.dinv32, nd);
+        if (l.dist_rows) {
+            // vectors that are all-gathered live in memory every rank maps (x32 | y32 | r32 | b32)
+            const size_t vb = (sizeof(float) * (size_t)std::max<i64>(nv, 1) + 255) & ~(size_t)255;
+            l.sym = sym_alloc(c, 4 * vb);
+            unsigned char* base = (unsigned char*)sym_data(l.sym);
+            l.x32 = (float*)base; l.y32 = (float*)(base + vb); l.r32 = (float*)(base + 2 * vb); l.b32 = (float*)(base + 3 * vb);
+            GL_CUDA(cudaMalloc(&l.d32, sizeof(float) * std::max<i64>(nv, 1)));
+            GL_CUDA(cudaMemsetAsync(l.d32, 0, sizeof(float) * std::max<i64>(nv, 1), c->stream));
+        } else
         for (float** v : {&l.x32, &l.b32, &l.r32, &l.d32, &l.y32}) {
             GL_CUDA(cudaMalloc(v, sizeof(float) * std::max<i64>(nv, 1)));
             GL_CUDA(cudaMemsetAsync(*v, 0, sizeof(float) * std::max<i64>(nv, 1), c->stream));
@@ -867,6 +942,7 @@ void build_fp32(glims_ctx* c, Amg* amg) {
 void free_level(Level& l) {
     if (l.owns_pat) free_pattern(l.pat);
     if (l.owns_A && l.A) cudaFree(l.A);
+    if (l.sym) { sym_free(l.sym); l.sym = nullptr; l.x32 = l.y32 = l.r32 = l.b32 = nullptr; }
     for (void* q : {(void*)l.dinv, (void*)l.agg, (void*)l.rvec, (void*)l.free_mask, (void*)l.mem_ptr, (void*)l.mem_idx,
                     (void*)l.X, (void*)l.x, (void*)l.b, (void*)l.r, (void*)l.d, (void*)l.A32, (void*)l.dinv32,
                     (void*)l.x32, (void*)l.b32, (void*)l.r32, (void*)l.d32, (void*)l.y32, (void*)l.A16})
@@ -877,6 +953,7 @@ void free_level(Level& l) {
 
 void amg_free(glims_ctx* c) {
     if (!c->amg) return;
+    amg_fused_free(c->amg);
     for (auto& l : c->amg->L) free_level(l);
     if (c->amg->coarse_inv) cudaFree(c->amg->coarse_inv);
     if (c->amg->coarse_inv32) cudaFree(c->amg->coarse_inv32);
@@ -912,24 +989,29 @@ void amg_setup(glims_ctx* c) {
     amg->L.push_back(l0);
 
     std::vector<double> Xl = X;              // positions of the current level's nodes
+    const bool dist = c->halo.active && c->halo.comm && c->halo.n_ranks > 1;
+    const int R = dist ? c->halo.n_ranks : 1, rank = dist ? c->halo.rank : 0;
+    amg->dist = dist; amg->n_ranks = R; amg->rank = rank;
+    std::vector<char> pad1;                  // dist: padding nodes of the global level 1
     int level = 0;
     while (true) {
         Level& l = amg->L[level];
         alloc_work(l);
         diag_inverse(c, l, level == 0 ? 0.0 : 1e-8);
         const int n = l.n;
-        const bool last = (n * l.bs <= 600) || level >= 12;
+        const bool last = ((n * l.bs <= 600) && !(dist && level == 0)) || level >= 12;
         if (last) break;
         // ---- aggregation on the host ---------------------------------------------------------------
         HostGraph g = download_graph(l.pat);
         std::vector<char> excl(n, 0);
         if (level == 0) for (int i = 0; i < n; ++i) excl[i] = (freem[i] == 0);
+        if (level == 1 && dist) for (int i = 0; i < n; ++i) excl[i] = pad1[i];      // padding nodes of the rank segments
         std::vector<int> agg;
         int na = aggregate(g, n, excl, agg);
-        if (na == 0 || na >= n) break;
+        if (!(dist && level == 0) && (na == 0 || na >= n)) break;
         // centroids, offsets, member lists
-        std::vector<double> Xc((i64)na * D, 0.0);
-        std::vector<int> cnt(na, 0);
+        std::vector<double> Xc((i64)std::max(na, 1) * D, 0.0);
+        std::vector<int> cnt(std::max(na, 1), 0);
         for (int i = 0; i < n; ++i) if (agg[i] >= 0) { cnt[agg[i]]++; for (int k = 0; k < D; ++k) Xc[(i64)agg[i] * D + k] += Xl[(i64)i * D + k]; }
         for (int I = 0; I < na; ++I) for (int k = 0; k < D; ++k) Xc[(i64)I * D + k] /= cnt[I];
         std::vector<double> rv((i64)std::max<i64>(l.n_cols, n) * D, 0.0);
@@ -940,7 +1022,42 @@ void amg_setup(glims_ctx* c) {
         { std::vector<int> pos(mptr.begin(), mptr.end() - 1); for (int i = 0; i < n; ++i) if (agg[i] >= 0) midx[pos[agg[i]]++] = i; }
         std::vector<int> aggfull(std::max<i64>(l.n_cols, n), -1);
         std::copy(agg.begin(), agg.end(), aggfull.begin());
-        l.bsc = bsc; l.nc = na;
+        int n_coarse = na;            // nodes of the next level
+        i64 seg = 0;
+        if (dist && level == 0) {
+            // Global numbering of the aggregates: rank r owns ids [r*seg, r*seg + na_r), seg = the largest rank count
+            // rounded up to a whole SELL slice (ids na_r .. seg-1 are padding nodes: identity rows, never aggregated).
+            long long m = ((long long)std::max(na, 1) + 31) / 32 * 32;
+            comm_allreduce_max_i64(c, &m, 1);
+            seg = m;
+            n_coarse = (int)(seg * R);
+            const int off = (int)(seg * rank);
+            for (int i = 0; i < n; ++i) if (aggfull[i] >= 0) aggfull[i] += off;
+            // ghost vertices: aggregate id and centroid of the owner, through the level-0 halo exchange
+            {
+                const int bsx = 1 + D;
+                std::vector<double> hx((i64)c->n_v * bsx, 0.0);
+                for (int i = 0; i < n; ++i) {
+                    hx[(i64)i * bsx] = (double)aggfull[i];
+                    if (agg[i] >= 0) for (int k = 0; k < D; ++k) hx[(i64)i * bsx + 1 + k] = Xc[(i64)agg[i] * D + k];
+                }
+                double* dx = nullptr;
+                GL_CUDA(cudaMalloc(&dx, sizeof(double) * hx.size()));
+                GL_CUDA(cudaMemcpy(dx, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice));
+                halo_exchange(c, dx, bsx);
+                GL_CUDA(cudaStreamSynchronize(c->stream));
+                GL_CUDA(cudaMemcpy(hx.data(), dx, sizeof(double) * hx.size(), cudaMemcpyDeviceToHost));
+                cudaFree(dx);
+                for (i64 j = n; j < c->n_v; ++j) {
+                    const int gid = (int)std::llround(hx[j * bsx]);
+                    aggfull[j] = gid;
+                    if (gid >= 0) for (int k = 0; k < D; ++k) rv[j * D + k] = X[j * D + k] - hx[j * bsx + 1 + k];
+                }
+            }
+            l.nc_off = off; l.nc_local = na;
+        }
+        l.bsc = bsc; l.nc = n_coarse;
+        if (!(dist && level == 0)) { l.nc_off = 0; l.nc_local = na; }
         GL_CUDA(cudaMalloc(&l.agg, sizeof(int) * aggfull.size()));
         GL_CUDA(cudaMemcpy(l.agg, aggfull.data(), sizeof(int) * aggfull.size(), cudaMemcpyHostToDevice));
         GL_CUDA(cudaMalloc(&l.rvec, sizeof(double) * rv.size()));
@@ -951,18 +1068,86 @@ void amg_setup(glims_ctx* c) {
         GL_CUDA(cudaMemcpy(l.mem_idx, midx.data(), sizeof(int) * midx.size(), cudaMemcpyHostToDevice));
         // ---- Galerkin operator on the device -------------------------------------------------------
         Level lc;
-        lc.bs = bsc; lc.n = na; lc.n_cols = na; lc.owns_pat = true; lc.owns_A = true;
+        lc.bs = bsc; lc.n = n_coarse; lc.n_cols = n_coarse; lc.owns_pat = true; lc.owns_A = true;
         unsigned long long *keys = nullptr, *ukeys = nullptr;
-        GL_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * std::max<i64>(l.pat.n_slots, 1)));
+        const i64 n_extra = (dist && level == 0) ? seg : 0;      // diagonal keys of this rank's whole segment
+        GL_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * std::max<i64>(l.pat.n_slots + n_extra, 1)));
         k_coarse_keys<<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, l.agg, keys);
-        build_pattern_from_keys(c->stream, keys, l.pat.n_slots, na, lc.pat, &ukeys);
-        cudaFree(keys);
-        GL_CUDA(cudaMalloc(&lc.A, sizeof(double) * lc.pat.n_slots * bsc * bsc));
-        GL_CUDA(cudaMemsetAsync(lc.A, 0, sizeof(double) * lc.pat.n_slots * bsc * bsc, c->stream));
-        if (D == 2) k_galerkin<2><<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, level == 0, l.A, l.agg, l.rvec, l.free_mask, ukeys, lc.pat.rowptr, lc.pat.slice_off, lc.A);
-        else k_galerkin<3><<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, level == 0, l.A, l.agg, l.rvec, l.free_mask, ukeys, lc.pat.rowptr, lc.pat.slice_off, lc.A);
-        GL_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(ukeys);
+        if (n_extra > 0) k_diag_keys<<<nblk(n_extra), TPB, 0, c->stream>>>(keys + l.pat.n_slots, (int)(seg * rank), (int)n_extra);
+        if (!(dist && level == 0)) {
+            build_pattern_from_keys(c->stream, keys, l.pat.n_slots, n_coarse, lc.pat, &ukeys);
+            cudaFree(keys);
+            GL_CUDA(cudaMalloc(&lc.A, sizeof(double) * lc.pat.n_slots * bsc * bsc));
+            GL_CUDA(cudaMemsetAsync(lc.A, 0, sizeof(double) * lc.pat.n_slots * bsc * bsc, c->stream));
+            if (D == 2) k_galerkin<2><<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, level == 0, l.A, l.agg, l.rvec, l.free_mask, ukeys, lc.pat.rowptr, lc.pat.slice_off, lc.A);
+            else k_galerkin<3><<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, level == 0, l.A, l.agg, l.rvec, l.free_mask, ukeys, lc.pat.rowptr, lc.pat.slice_off, lc.A);
+            GL_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(ukeys);
+            if (dist) {
+                // levels >= 2 are built redundantly; Galerkin sums use atomics, so make the bits identical everywhere
+                std::vector<long long> cntv(R, 0);
+                cntv[0] = (long long)lc.pat.n_slots * bsc * bsc;
+                comm_allgatherv(c, lc.A, lc.A, cntv, sizeof(double));
+            }
+        } else {
+            // this rank's rows of the global operator (rows of the other segments stay empty) ...
+            SellPattern ploc;
+            build_pattern_from_keys(c->stream, keys, l.pat.n_slots + n_extra, n_coarse, ploc, &ukeys);
+            cudaFree(keys);
+            double* Aloc = nullptr;
+            const int bb = bsc * bsc;
+            GL_CUDA(cudaMalloc(&Aloc, sizeof(double) * std::max<i64>(ploc.n_slots, 1) * bb));
+            GL_CUDA(cudaMemsetAsync(Aloc, 0, sizeof(double) * std::max<i64>(ploc.n_slots, 1) * bb, c->stream));
+            if (D == 2) k_galerkin<2><<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, true, l.A, l.agg, l.rvec, l.free_mask, ukeys, ploc.rowptr, ploc.slice_off, Aloc);
+            else k_galerkin<3><<<l.pat.n_slices, 128, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.col, l.pat.n_rows, true, l.A, l.agg, l.rvec, l.free_mask, ukeys, ploc.rowptr, ploc.slice_off, Aloc);
+            // ... gathered from all ranks: unique keys are in CSR order, rank segments are contiguous row ranges, so the
+            // concatenation in rank order is the CSR order of the global matrix
+            const i64 nnz_loc = ploc.nnzb;
+            double* vloc = nullptr;
+            GL_CUDA(cudaMalloc(&vloc, sizeof(double) * std::max<i64>(nnz_loc, 1) * bb));
+            k_sell_to_csr<<<nblk(n_coarse), TPB, 0, c->stream>>>(ploc.rowptr, ploc.slice_off, n_coarse, bb, Aloc, vloc);
+            GL_CUDA(cudaStreamSynchronize(c->stream));
+            std::vector<long long> counts;
+            comm_allgather_i64(c, nnz_loc, counts);
+            i64 nnz_tot = 0;
+            for (long long v : counts) nnz_tot += v;
+            unsigned long long* gkeys = nullptr;
+            double* gvals = nullptr;
+            GL_CUDA(cudaMalloc(&gkeys, sizeof(unsigned long long) * std::max<i64>(nnz_tot, 1)));
+            GL_CUDA(cudaMalloc(&gvals, sizeof(double) * std::max<i64>(nnz_tot, 1) * bb));
+            comm_allgatherv(c, ukeys, gkeys, counts, sizeof(unsigned long long));
+            comm_allgatherv(c, vloc, gvals, counts, sizeof(double) * bb);
+            cudaFree(ukeys); cudaFree(vloc); cudaFree(Aloc);
+            free_pattern(ploc);
+            build_pattern_from_keys(c->stream, gkeys, nnz_tot, n_coarse, lc.pat, nullptr);       // consumes gkeys (already sorted + unique)
+            cudaFree(gkeys);
+            if (lc.pat.nnzb != nnz_tot) throw GlError(GLIMS_ERR_NCCL, "amg: gathered level-1 operator has duplicate blocks");
+            GL_CUDA(cudaMalloc(&lc.A, sizeof(double) * lc.pat.n_slots * bb));
+            GL_CUDA(cudaMemsetAsync(lc.A, 0, sizeof(double) * lc.pat.n_slots * bb, c->stream));
+            k_csr_to_sell<<<nblk(n_coarse), TPB, 0, c->stream>>>(lc.pat.rowptr, lc.pat.slice_off, n_coarse, bb, gvals, lc.A);
+            GL_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(gvals);
+            lc.dist_rows = true; lc.row0 = (int)(seg * rank); lc.rows = (int)seg;
+            // node positions and the padding mask of the global level (identical on every rank)
+            std::vector<double> Xg((i64)n_coarse * D, 0.0);
+            {
+                double *dl = nullptr, *dg = nullptr;
+                std::vector<double> mine((i64)seg * D, 0.0);
+                std::copy(Xc.begin(), Xc.begin() + (i64)na * D, mine.begin());
+                GL_CUDA(cudaMalloc(&dl, sizeof(double) * mine.size()));
+                GL_CUDA(cudaMalloc(&dg, sizeof(double) * Xg.size()));
+                GL_CUDA(cudaMemcpy(dl, mine.data(), sizeof(double) * mine.size(), cudaMemcpyHostToDevice));
+                std::vector<long long> eq(R, (long long)seg * D);
+                comm_allgatherv(c, dl, dg, eq, sizeof(double));
+                GL_CUDA(cudaMemcpy(Xg.data(), dg, sizeof(double) * Xg.size(), cudaMemcpyDeviceToHost));
+                cudaFree(dl); cudaFree(dg);
+            }
+            std::vector<long long> nas;
+            comm_allgather_i64(c, na, nas);
+            pad1.assign(n_coarse, 0);
+            for (int r = 0; r < R; ++r) for (i64 i = nas[r]; i < seg; ++i) pad1[(i64)r * seg + i] = 1;
+            Xc.swap(Xg);
+        }
         amg->L.push_back(lc);
         Xl.swap(Xc);
         ++level;
@@ -1013,6 +1198,14 @@ void amg_setup(glims_ctx* c) {
     // ---- smoother spectra ----------------------------------------------------------------------------
     for (size_t li = 0; li + 1 < amg->L.size(); ++li) estimate_lmax(c, amg->L[li]);
     GL_CUDA(cudaStreamSynchronize(c->stream));
+    if (dist) {
+        // one smoother for the whole mesh: the level-0 spectrum estimate is rank-local, take the largest; the other
+        // levels are replicated (identical data, deterministic kernels), agree on them anyway
+        std::vector<double> lm(amg->L.size(), 0.0);
+        for (size_t li = 0; li < amg->L.size(); ++li) lm[li] = amg->L[li].lmax;
+        comm_allreduce_max_f64(c, lm.data(), (int)lm.size());
+        for (size_t li = 0; li < amg->L.size(); ++li) amg->L[li].lmax = lm[li];
+    }
     build_fp32(c, amg);
     if (std::getenv("GLIMS_VERBOSE"))
         for (size_t li = 0; li < amg->L.size(); ++li) {
@@ -1020,6 +1213,14 @@ void amg_setup(glims_ctx* c) {
             fprintf(stderr, "glims amg level %zu: %d nodes x %d dofs, %lld blocks (%lld slots, max row %d), lmax %.3f\n", li, l.n, l.bs,
                     (long long)l.pat.nnzb, (long long)l.pat.n_slots, l.pat.max_w, l.lmax);
         }
+}
+
+// throws if a device-side wait of the preconditioner timed out (fused coarse kernel barrier, level-1 all-gather)
+void amg_check(glims_ctx* c) {
+    Amg* amg = c->amg;
+    if (!amg) return;
+    if (amg_fused_failed(amg)) throw GlError(GLIMS_ERR_CUDA, "amg: the fused coarse-level kernel timed out at a grid barrier (grid not co-resident)");
+    for (auto& l : amg->L) if (l.sym && sym_check(l.sym)) throw GlError(GLIMS_ERR_NCCL, "amg: level-1 all-gather timed out waiting for a peer rank");
 }
 
 // one fused smoother step on the fine level with the hierarchy's own buffers (roofline bench, glims_time_kernel 6)
@@ -1033,6 +1234,7 @@ bool amg_time_fine_step(glims_ctx* c) {
 
 void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32) {
     Amg* amg = c->amg;
+    if (amg->dist) fp32 = true;      // partitioned mesh: the hierarchy with the replicated level 1 exists in FP32 only
     if (!fp32) {
         if (amg->L.size() == 1) {     // tiny problem: the dense inverse is the whole hierarchy
             k_dense_matvec<<<(amg->coarse_m + 7) / 8, 256, 0, c->stream>>>(amg->coarse_inv, r, z, amg->coarse_m);

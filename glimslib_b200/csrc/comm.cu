@@ -159,6 +159,52 @@ k_allreduce(const P2PDev* __restrict__ P, double* __restrict__ scal, int slot0, 
     if (threadIdx.x == 0) *seqp = seq;
 }
 
+// ---- symmetric buffers: one allocation per rank that every rank maps (AMG level-1 vectors, amg.cu) ----------------------
+// layout: [0,64) u64 flag[rank] | [64,72) u64 seq | [72,76) u32 pushed | [76,80) i32 error | [80,84) u32 left | data from 256
+constexpr size_t SYM_DATA = 256;
+struct SymDev {
+    int n_ranks, rank;
+    unsigned char* base[P2P_MAX_RANKS];
+};
+
+// In-place allgather of [n_ranks][seg] floats at byte offset `off` of the symmetric buffer: every rank pushes its own
+// segment into the same place of every peer's buffer, publishes a sequence number and waits for the peers' numbers.
+// Same protocol and exit discipline as k_halo; no copy-out: the data land where the consumer kernels read them.
+__global__ void __launch_bounds__(256)
+k_allgather32(const SymDev* __restrict__ S, size_t off, long long seg) {
+    unsigned char* me = S->base[S->rank];
+    unsigned long long* seqp = (unsigned long long*)(me + 64);
+    int* err = (int*)(me + 76);
+    const unsigned long long seq = *seqp + 1;
+    const int R = S->n_ranks, rank = S->rank;
+    const float* src = (const float*)(me + SYM_DATA + off) + (size_t)rank * seg;
+    const long long n4 = seg >> 2;               // seg is a multiple of 32 floats
+    const long long total = n4 * (R - 1);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t / n4);
+        const long long k = t - q * n4;
+        const int r = q < rank ? q : q + 1;
+        float4* dst = (float4*)((float*)(S->base[r] + SYM_DATA + off) + (size_t)rank * seg);
+        dst[k] = ((const float4*)src)[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    unsigned* done = (unsigned*)(me + 72);
+    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < R && threadIdx.x != rank)
+            st_release_sys((unsigned long long*)(S->base[threadIdx.x]) + rank, seq);
+    }
+    if (threadIdx.x < R && threadIdx.x != rank)
+        spin_until((const unsigned long long*)me + threadIdx.x, seq, err);
+    __syncthreads();
+    unsigned* gone = (unsigned*)(me + 80);
+    if (threadIdx.x == 0 && atomicAdd(gone, 1u) == gridDim.x - 1) { *done = 0; *gone = 0; __threadfence(); *seqp = seq; }
+}
+
 __global__ void k_pack(const double* __restrict__ x, const int* __restrict__ idx, i64 n, int bs, double* buf) {
     i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     if (t >= n * bs) return;
@@ -335,6 +381,147 @@ void allreduce_scalars(glims_ctx* c, int slot0, int n) {
         return;
     }
     GL_NCCL(ncclAllReduce(c->scal + slot0, c->scal + slot0, n, ncclDouble, ncclSum, (ncclComm_t)h.comm, c->stream));
+}
+
+// ---- symmetric buffers (host side) ------------------------------------------------------------------------------------
+struct SymBuf {
+    unsigned char* mine = nullptr;
+    size_t bytes = 0;
+    std::vector<void*> opened;
+    SymDev host;
+    SymDev* dev = nullptr;
+    bool p2p = false;       // every rank could map every other rank's buffer
+};
+
+// Collective over the context's NCCL communicator.  `bytes` of payload (zeroed).
+void* sym_alloc(glims_ctx* c, size_t bytes) {
+    Halo& h = c->halo;
+    SymBuf* sb = new SymBuf();
+    sb->bytes = SYM_DATA + ((bytes + 255) & ~(size_t)255);
+    GL_CUDA(cudaMalloc(&sb->mine, sb->bytes));
+    GL_CUDA(cudaMemset(sb->mine, 0, sb->bytes));
+    memset(&sb->host, 0, sizeof sb->host);
+    sb->host.n_ranks = h.n_ranks; sb->host.rank = h.rank;
+    sb->host.base[h.rank] = sb->mine;
+    const int R = h.n_ranks;
+    if (!h.comm || R <= 1 || R > P2P_MAX_RANKS) return sb;
+    ncclComm_t comm = (ncclComm_t)h.comm;
+    int ok = (p2p_of(c) != nullptr);            // only where the halo windows could be mapped as well
+    cudaIpcMemHandle_t mine_h;
+    memset(&mine_h, 0, sizeof mine_h);
+    if (ok && cudaIpcGetMemHandle(&mine_h, sb->mine) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    cudaIpcMemHandle_t* d_all = nullptr;
+    GL_CUDA(cudaMalloc(&d_all, sizeof(cudaIpcMemHandle_t) * R));
+    GL_CUDA(cudaMemcpy(d_all + h.rank, &mine_h, sizeof mine_h, cudaMemcpyHostToDevice));
+    GL_NCCL(ncclAllGather(d_all + h.rank, d_all, sizeof(cudaIpcMemHandle_t), ncclChar, comm, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<cudaIpcMemHandle_t> all(R);
+    GL_CUDA(cudaMemcpy(all.data(), d_all, sizeof(cudaIpcMemHandle_t) * R, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < R && ok; ++r) {
+        if (r == h.rank) continue;
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        sb->opened.push_back(q);
+        sb->host.base[r] = (unsigned char*)q;
+    }
+    int* d_ok = (int*)d_all;
+    GL_CUDA(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    GL_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, c->stream));      // also the "everybody has zeroed" rendezvous
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    GL_CUDA(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    sb->p2p = ok != 0;
+    if (sb->p2p) {
+        GL_CUDA(cudaMalloc(&sb->dev, sizeof(SymDev)));
+        GL_CUDA(cudaMemcpy(sb->dev, &sb->host, sizeof(SymDev), cudaMemcpyHostToDevice));
+    }
+    return sb;
+}
+
+void sym_free(void* p) {
+    SymBuf* sb = (SymBuf*)p;
+    if (!sb) return;
+    for (void* q : sb->opened) cudaIpcCloseMemHandle(q);
+    if (sb->dev) cudaFree(sb->dev);
+    if (sb->mine) cudaFree(sb->mine);
+    delete sb;
+}
+
+void* sym_data(void* p) { return p ? ((SymBuf*)p)->mine + SYM_DATA : nullptr; }
+
+bool sym_check(void* p) {           // true: a wait timed out
+    SymBuf* sb = (SymBuf*)p;
+    if (!sb || !sb->p2p) return false;
+    int err = 0;
+    cudaMemcpy(&err, sb->mine + 76, sizeof(int), cudaMemcpyDeviceToHost);
+    return err != 0;
+}
+
+// buf = float vector of n_ranks * seg entries living at `buf` inside the symmetric buffer; every rank owns segment `rank`
+void allgather_f32(glims_ctx* c, void* p, float* buf, i64 seg) {
+    Halo& h = c->halo;
+    SymBuf* sb = (SymBuf*)p;
+    if (!sb || !h.comm || h.n_ranks <= 1) return;
+    if (sb->p2p && h.p2p_enabled) {
+        const size_t off = (size_t)((unsigned char*)buf - (sb->mine + SYM_DATA));
+        const i64 total = (seg >> 2) * (h.n_ranks - 1);
+        int g = (int)std::min<i64>(std::max<i64>((total + 255) / 256, 1), 148);
+        k_allgather32<<<g, 256, 0, c->stream>>>(sb->dev, off, seg);
+        c->launches++;
+        return;
+    }
+    GL_NCCL(ncclAllGather(buf + (size_t)h.rank * seg, buf, seg, ncclFloat, (ncclComm_t)h.comm, c->stream));
+}
+
+// setup-time helpers for amg.cu (collective, synchronous)
+void comm_allreduce_max_i64(glims_ctx* c, long long* v, int n) {
+    Halo& h = c->halo;
+    if (!h.comm || h.n_ranks <= 1) return;
+    long long* d = nullptr;
+    GL_CUDA(cudaMalloc(&d, sizeof(long long) * n));
+    GL_CUDA(cudaMemcpy(d, v, sizeof(long long) * n, cudaMemcpyHostToDevice));
+    GL_NCCL(ncclAllReduce(d, d, n, ncclInt64, ncclMax, (ncclComm_t)h.comm, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    GL_CUDA(cudaMemcpy(v, d, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+}
+void comm_allreduce_max_f64(glims_ctx* c, double* v, int n) {
+    Halo& h = c->halo;
+    if (!h.comm || h.n_ranks <= 1) return;
+    double* d = nullptr;
+    GL_CUDA(cudaMalloc(&d, sizeof(double) * n));
+    GL_CUDA(cudaMemcpy(d, v, sizeof(double) * n, cudaMemcpyHostToDevice));
+    GL_NCCL(ncclAllReduce(d, d, n, ncclDouble, ncclMax, (ncclComm_t)h.comm, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    GL_CUDA(cudaMemcpy(v, d, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+}
+// counts[r] = number of `elem_bytes`-sized items rank r contributes; dst (device) receives all items in rank order
+void comm_allgatherv(glims_ctx* c, const void* src_dev, void* dst_dev, const std::vector<long long>& counts, size_t elem_bytes) {
+    Halo& h = c->halo;
+    ncclComm_t comm = (ncclComm_t)h.comm;
+    size_t off = 0;
+    GL_NCCL(ncclGroupStart());
+    for (int r = 0; r < h.n_ranks; ++r) {
+        const size_t nbytes = (size_t)counts[r] * elem_bytes;
+        if (nbytes > 0)
+            GL_NCCL(ncclBroadcast(r == h.rank ? src_dev : (const void*)((unsigned char*)dst_dev + off), (unsigned char*)dst_dev + off,
+                                  nbytes, ncclChar, r, comm, c->stream));
+        off += nbytes;
+    }
+    GL_NCCL(ncclGroupEnd());
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+}
+void comm_allgather_i64(glims_ctx* c, long long mine, std::vector<long long>& all) {
+    Halo& h = c->halo;
+    all.assign(h.n_ranks, 0);
+    long long* d = nullptr;
+    GL_CUDA(cudaMalloc(&d, sizeof(long long) * h.n_ranks));
+    GL_CUDA(cudaMemcpy(d + h.rank, &mine, sizeof(long long), cudaMemcpyHostToDevice));
+    GL_NCCL(ncclAllGather(d + h.rank, d, 1, ncclInt64, (ncclComm_t)h.comm, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    GL_CUDA(cudaMemcpy(all.data(), d, sizeof(long long) * h.n_ranks, cudaMemcpyDeviceToHost));
+    cudaFree(d);
 }
 
 extern "C" {

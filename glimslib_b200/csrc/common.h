@@ -221,6 +221,7 @@ void launch_permute(glims_ctx* c, const double* src, double* dst, const i64* per
 void amg_setup(glims_ctx* c);
 void amg_free(glims_ctx* c);
 void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32);
+void amg_check(glims_ctx* c);              // throws if a device-side wait inside the V-cycle timed out
 bool amg_time_fine_step(glims_ctx* c);     // false: no FP32 hierarchy yet   // z = M^-1 r on K_uu ([n_v][dim] vectors)
 
 // ---------------- comm.cu
@@ -230,3 +231,15 @@ void allreduce_scalars(glims_ctx* c, int slot0, int n);      // in-place sum ove
 void comm_free(glims_ctx* c);                                // peer windows (NCCL communicator is left to process exit)
 void comm_check(glims_ctx* c);                               // throws if a peer-memory wait timed out
 void solver_free_graphs(glims_ctx* c);                       // solver.cu: drop captured PCG graphs (transport changed)
+// symmetric buffers: one allocation per rank mapped by every rank (collective alloc); allgather_f32 gathers, in place, a
+// float vector [n_ranks][seg] living inside such a buffer (peer-memory pushes, or ncclAllGather when peer memory is off)
+void* sym_alloc(glims_ctx* c, size_t bytes);
+void sym_free(void* sb);
+void* sym_data(void* sb);
+bool sym_check(void* sb);
+void allgather_f32(glims_ctx* c, void* sb, float* buf, i64 seg);
+// setup-time collectives (synchronous)
+void comm_allreduce_max_i64(glims_ctx* c, long long* v, int n);
+void comm_allreduce_max_f64(glims_ctx* c, double* v, int n);
+void comm_allgatherv(glims_ctx* c, const void* src_dev, void* dst_dev, const std::vector<long long>& counts, size_t elem_bytes);
+void comm_allgather_i64(glims_ctx* c, long long mine, std::vector<long long>& all);

@@ -917,6 +917,7 @@ int glims_step(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, glims_
     }
     GL_CUDA(cudaStreamSynchronize(c->stream));
     comm_check(c);
+    amg_check(c);
     API_END
 }
 

@@ -26,10 +26,11 @@ def main():
     eng.set_prev(x0)
     eng.set_state(np.zeros_like(x0))
     kw = dict(snes_rtol=1e-10, snes_atol=1e-14, ksp_rtol=1e-12)
-    sols = []
+    sols, its = [], []
     for _ in range(3):
         st = eng.step(1, **kw)[0]
         assert st["converged"] == 1
+        its.append(st["krylov_its_u"])
         sols.append(D.gather_owned(lm, eng.get_state(), dist))
     if rank == 0:
         ref = W.build_engine(w, device=local)
@@ -41,8 +42,9 @@ def main():
                            fem.Materials(t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4]), w["dt"],
                            bc_dofs=w["bc_dofs"], bc_vals=w["bc_vals"])
         recs, _ = osolver.run(prob, w["x0"], 3, linear="gmres_ilu", rtol=1e-12, atol=1e-15, ksp_rtol=1e-13)
+        its1 = []
         for k in range(3):
-            ref.step(1, **kw)
+            its1.append(ref.step(1, **kw)[0]["krylov_its_u"])
             a, b, o = sols[k].reshape(-1, 4), ref.get_state().reshape(-1, 4), recs[k + 1][2].reshape(-1, 4)
             for name, sl in (("u", slice(0, 3)), ("c", slice(3, 4))):
                 e1 = np.linalg.norm(a[:, sl] - b[:, sl]) / np.linalg.norm(b[:, sl])
@@ -50,6 +52,7 @@ def main():
                 print("step %d %s: vs 1-GPU %.2e, vs oracle %.2e" % (k + 1, name, e1, e2))
                 assert e1 < 1e-8 and e2 < 1e-7, (k, name, e1, e2)
         ref.close()
+        print("K_uu PCG iterations per step: %d ranks %r, one GPU %r" % (world, its, its1))
         print("DIST_CHECK_OK world=%d" % world)
     dist.barrier()
     eng.close()
