@@ -819,6 +819,37 @@ struct ChebCoef {                 // Chebyshev recurrence for the interval [rati
 // in l.y32 leaves the result in x.
 #include "amg_fused.cuh"
 
+void vcycle32(glims_ctx* c, Amg* amg, int li, float* b, float* x);
+
+// cur(level li) += P * V-cycle(levels li+1 ..)(P^T r32(level li)): the coarse-grid correction below level li
+void coarse_correction32(glims_ctx* c, Amg* amg, int li, float* cur) {
+    Level& l = amg->L[li];
+    Level& lc = amg->L[li + 1];
+    const int D = amg->dim;
+    const bool l0 = (li == 0);
+    if (li >= 1 && amg_fused_run(c, amg, li, cur)) {
+        // levels li+1 .. coarsest ran in one persistent kernel: restriction of r32, the coarse V-cycle and the
+        // prolongation into `cur` included (amg_fused.cuh)
+        return;
+    }
+    float* rc = lc.b32 + (i64)l.nc_off * lc.bs;
+    const int nca = l.nc_local;
+    if (nca >= 16384) {      // many aggregates: thread per aggregate; few: warp per aggregate (latency)
+        if (D == 2) k_restrict32_serial<2><<<nblk(nca), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
+        else k_restrict32_serial<3><<<nblk(nca), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
+    } else if (nca > 0) {
+        if (D == 2) k_restrict32<2><<<nblk(nca, TPB / 32), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
+        else k_restrict32<3><<<nblk(nca, TPB / 32), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
+    }
+    c->launches++;
+    vcycle32(c, amg, li + 1, lc.b32, lc.x32);
+    // level 1 of a partitioned mesh: every rank prolongs ALL nodes (its copy of `cur` is complete after the gather
+    // in vcycle32 and x of level 2 is identical everywhere), so the first post-smoothing step needs no exchange
+    if (D == 2) k_prolong_add32<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
+    else k_prolong_add32<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
+    c->launches++;
+}
+
 void vcycle32(glims_ctx* c, Amg* amg, int li, float* b, float* x) {
     Level& l = amg->L[li];
     const int D = amg->dim;
@@ -860,27 +891,7 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, float* b, float* x) {
     gather(cur);
     spmv32(c, l, cur, l.r32, b);
     gather(l.r32);                    // level 1 of a partitioned mesh: what follows runs redundantly on every rank
-    if (li >= 1 && amg_fused_run(c, amg, li, cur)) {
-        // levels li+1 .. coarsest ran in one persistent kernel: restriction of r32, the coarse V-cycle and the
-        // prolongation into `cur` included (amg_fused.cuh)
-    } else {
-        float* rc = lc.b32 + (i64)l.nc_off * lc.bs;
-        const int nca = l.nc_local;
-        if (nca >= 16384) {      // many aggregates: thread per aggregate; few: warp per aggregate (latency)
-            if (D == 2) k_restrict32_serial<2><<<nblk(nca), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
-            else k_restrict32_serial<3><<<nblk(nca), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
-        } else if (nca > 0) {
-            if (D == 2) k_restrict32<2><<<nblk(nca, TPB / 32), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
-            else k_restrict32<3><<<nblk(nca, TPB / 32), TPB, 0, c->stream>>>(nca, l.mem_ptr, l.mem_idx, l0, l.rvec, l.free_mask, l.r32, rc);
-        }
-        c->launches++;
-        vcycle32(c, amg, li + 1, lc.b32, lc.x32);
-        // level 1 of a partitioned mesh: every rank prolongs ALL nodes (its copy of `cur` is complete after the gather
-        // above and x of level 2 is identical everywhere), so the first post-smoothing step needs no exchange
-        if (D == 2) k_prolong_add32<2><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
-        else k_prolong_add32<3><<<nblk(l.n), TPB, 0, c->stream>>>(l.n, l.agg, l0, l.rvec, l.free_mask, lc.x32, cur);
-        c->launches++;
-    }
+    coarse_correction32(c, amg, li, cur);
     {   // post-smoothing
         ChebCoef cc(l.lmax, amg->cheb_ratio);
         for (int k = 0; k < degree; ++k) {
@@ -1221,6 +1232,18 @@ void amg_check(glims_ctx* c) {
     if (!amg) return;
     if (amg_fused_failed(amg)) throw GlError(GLIMS_ERR_CUDA, "amg: the fused coarse-level kernel timed out at a grid barrier (grid not co-resident)");
     for (auto& l : amg->L) if (l.sym && sym_check(l.sym)) throw GlError(GLIMS_ERR_NCCL, "amg: level-1 all-gather timed out waiting for a peer rank");
+}
+
+// coarse-grid correction below level 1 with the hierarchy's own buffers (glims_time_kernel 9): the fused persistent kernel,
+// or the launch sequence it replaces with GLIMS_AMG_FUSED=0
+bool amg_time_coarse(glims_ctx* c) {
+    Amg* amg = c->amg;
+    if (!amg || amg->L.size() < 3 || !amg->L[1].y32) return false;
+    // the iterate buffer the V-cycle holds at this point (after `coarse_degree` - 1 ping-pong steps from y32)
+    float* cur = ((amg->coarse_degree - 1) & 1) ? amg->L[1].x32 : amg->L[1].y32;
+    coarse_correction32(c, amg, 1, cur);
+    if (std::getenv("GLIMS_VERBOSE")) { cudaStreamSynchronize(c->stream); amg_fused_print_phases(amg); }
+    return true;
 }
 
 // one fused smoother step on the fine level with the hierarchy's own buffers (roofline bench, glims_time_kernel 6)

@@ -31,6 +31,7 @@ struct FusedPlan {
     FusedLevel L[FUSED_MAX_LEVELS];
     FusedPhase P[FUSED_MAX_PHASES];
     unsigned* bar;          // [0] arrivals, [1] generation, [2] error (a barrier wait timed out)
+    unsigned long long* tstamp;     // [n_phases+1] %globaltimer of CTA 0 at the start and after every phase (diagnostics)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -63,31 +64,46 @@ __device__ __forceinline__ void fused_grid_barrier(unsigned* bar) {
     __syncthreads();
 }
 
-// component i of (A x) for row `lane` of a slice; x through L2
+// component i of (A x) for row `lane` of a slice; x through L2.  Eight block columns in flight: a row of ~24 blocks is
+// three rounds of dependent loads (column index -> x), which is what a phase costs on these latency-bound levels.
 template <int BS>
 __device__ __forceinline__ float fused_row_dot(const i64 base, const int w, const int* __restrict__ col,
                                                const float* __restrict__ A, const float* x, const int i, const int lane) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int U = 8;
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.f;
     int j = 0;
-    for (; j + 3 < w; j += 4) {
-        int cc[4];
+    for (; j + U - 1 < w; j += U) {
+        int cc[U];
+        float av[U][BS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) cc[u] = __ldg(&col[base + (i64)(j + u) * 32 + lane]);
+        for (int u = 0; u < U; ++u) cc[u] = __ldg(&col[base + (i64)(j + u) * 32 + lane]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const float* Au = A + (base + (i64)(j + u) * 32) * (BS * BS) + (i * BS) * 32 + lane;
 #pragma unroll
-            for (int b = 0; b < BS; ++b) acc[u] += __ldg(&Au[b * 32]) * __ldcg(&x[(i64)cc[u] * BS + b]);
+            for (int b = 0; b < BS; ++b) av[u][b] = __ldg(&Au[b * 32]);
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc[u] += av[u][b] * __ldcg(&x[(i64)cc[u] * BS + b]);
     }
     for (; j < w; ++j) {
         const int c0 = __ldg(&col[base + (i64)j * 32 + lane]);
         const float* A0 = A + (base + (i64)j * 32) * (BS * BS) + (i * BS) * 32 + lane;
 #pragma unroll
-        for (int b = 0; b < BS; ++b) acc[0] += __ldg(&A0[b * 32]) * __ldcg(&x[(i64)c0 * BS + b]);
+        for (int b = 0; b < BS; ++b) acc[j & (U - 1)] += __ldg(&A0[b * 32]) * __ldcg(&x[(i64)c0 * BS + b]);
     }
-    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) s += acc[u];
+    return s;
 }
+
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int D>
 __global__ void __launch_bounds__(32 * ((D == 2) ? 3 : 6))
@@ -98,6 +114,18 @@ k_amg_fused(const FusedPlan* __restrict__ plan) {
     const int gtid = blockIdx.x * NT + threadIdx.x, gthreads = gridDim.x * NT;
     const int gwarp = blockIdx.x * BS + wi, gwarps = gridDim.x * BS;
     const int n_phases = plan->n_phases;
+    if (gtid == 0) plan->tstamp[0] = global_ns();
+    // The matrices of these levels were evicted from L2 by the fine-level streams of the same PCG iteration and every
+    // phase is a chain of dependent loads: pull them (and the transfer maps) back into L2 while phase 0 runs.
+    for (int k = 1; k + 1 < plan->n_levels; ++k) {
+        const FusedLevel& F = plan->L[k];
+        const i64 n_slots = F.slice_off[F.n_slices];
+        const char* a = (const char*)F.A;
+        const i64 nb_a = n_slots * (i64)(BS * BS) * 4, nb_c = n_slots * 4, nb_d = (i64)F.n * BS * BS * 4;
+        for (i64 o = (i64)gtid * 128; o < nb_a; o += (i64)gthreads * 128) prefetch_l2(a + o);
+        for (i64 o = (i64)gtid * 128; o < nb_c; o += (i64)gthreads * 128) prefetch_l2((const char*)F.col + o);
+        for (i64 o = (i64)gtid * 128; o < nb_d; o += (i64)gthreads * 128) prefetch_l2((const char*)F.dinv + o);
+    }
     for (int ph = 0; ph < n_phases; ++ph) {
         const FusedPhase P = plan->P[ph];
         const FusedLevel& L = plan->L[P.lvl];
@@ -186,12 +214,15 @@ k_amg_fused(const FusedPlan* __restrict__ plan) {
             for (int t = gtid; t < L.n * BS; t += gthreads) P.dst[t] = __ldcg(&P.src[t]);
         }
         if (ph + 1 < n_phases) fused_grid_barrier(plan->bar);
+        if (gtid == 0) plan->tstamp[ph + 1] = global_ns();
     }
 }
 
 struct FusedHost {
     FusedPlan* dev = nullptr;
     unsigned* bar = nullptr;
+    unsigned long long* tstamp = nullptr;
+    std::vector<int> ops, lvls;
     int grid = 0, top_level = 0;
     float* top_cur = nullptr;       // the iterate buffer of the level above that the plan prolongs into
     int n_phases = 0;
@@ -202,6 +233,7 @@ static void amg_fused_free(Amg* amg) {
     if (!f) return;
     if (f->dev) cudaFree(f->dev);
     if (f->bar) cudaFree(f->bar);
+    if (f->tstamp) cudaFree(f->tstamp);
     delete f;
     amg->fused = nullptr;
 }
@@ -264,6 +296,10 @@ static FusedHost* amg_fused_build(glims_ctx* c, Amg* amg, int top, float* cur) {
     GL_CUDA(cudaMalloc(&f->bar, 4 * sizeof(unsigned)));
     GL_CUDA(cudaMemset(f->bar, 0, 4 * sizeof(unsigned)));
     P->bar = f->bar;
+    GL_CUDA(cudaMalloc(&f->tstamp, (FUSED_MAX_PHASES + 1) * sizeof(unsigned long long)));
+    GL_CUDA(cudaMemset(f->tstamp, 0, (FUSED_MAX_PHASES + 1) * sizeof(unsigned long long)));
+    P->tstamp = f->tstamp;
+    for (int i = 0; i < np; ++i) { f->ops.push_back(P->P[i].op); f->lvls.push_back(P->P[i].lvl); }
     GL_CUDA(cudaMalloc(&f->dev, sizeof(FusedPlan)));
     GL_CUDA(cudaMemcpy(f->dev, P, sizeof(FusedPlan), cudaMemcpyHostToDevice));
     // grid: enough CTAs for the widest phase, never more than can be co-resident (the barrier spins)
@@ -289,6 +325,18 @@ static bool amg_fused_failed(Amg* amg) {
     unsigned e = 0;
     cudaMemcpy(&e, f->bar + 2, sizeof(unsigned), cudaMemcpyDeviceToHost);
     return e != 0;
+}
+
+// per-phase durations of the last launch (GLIMS_VERBOSE diagnostics)
+static void amg_fused_print_phases(Amg* amg) {
+    FusedHost* f = amg ? (FusedHost*)amg->fused : nullptr;
+    if (!f || !f->tstamp) return;
+    std::vector<unsigned long long> t(f->n_phases + 1);
+    cudaMemcpy(t.data(), f->tstamp, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost);
+    static const char* names[] = {"restrict", "first", "step", "resid", "dense", "prolong", "copy"};
+    fprintf(stderr, "glims amg fused kernel: grid %d, %d phases, %.1f us:", f->grid, f->n_phases, (t.back() - t[0]) * 1e-3);
+    for (int i = 0; i < f->n_phases; ++i) fprintf(stderr, " %s@%d %.1f", names[f->ops[i]], f->lvls[i], (t[i + 1] - t[i]) * 1e-3);
+    fprintf(stderr, "\n");
 }
 
 // true: levels li+1.. ran fused (r32 of level li restricted, result prolonged into cur)

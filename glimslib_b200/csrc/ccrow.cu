@@ -28,6 +28,7 @@
 #include <thrust/iterator/transform_iterator.h>
 #include <thrust/reduce.h>
 #include <algorithm>
+#include <cstdlib>
 
 struct CcMap {
     bool ok = false;
@@ -285,6 +286,107 @@ k_cc_rows(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, co
     if (F && r < n_rows) F[(i64)r * NB + D] = fc - mcp[r] - (fext ? fext[(i64)r * NB + D] : 0.0);
 }
 
+// ---- bulk-copy (TMA) variant ---------------------------------------------------------------------------------------------
+// The (rho|K|, columns) list of a slice is two contiguous runs of global memory (pw*256 B and pw*128 B).  Lane 0 hands both to
+// the bulk-copy engine (cp.async.bulk ... mbarrier::complete_tx) and the warp gathers the slice's column values while the
+// copies fly; the pair loop then reads only shared memory.  No register staging, no long-scoreboard stall inside the loop,
+// and ~10 KB in flight per warp instead of what fits in registers.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int D, bool WK>
+__global__ void __launch_bounds__(CC_TPB)
+k_cc_rows_tma(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col, int n_rows,
+              int n_slices, const i64* __restrict__ pl_off, const int* __restrict__ pl_w, const double* __restrict__ prv,
+              const unsigned* __restrict__ ppa, const double* __restrict__ Klin,
+              const double* __restrict__ mcp, const double* __restrict__ fext, const double* __restrict__ x, double dt,
+              int max_w, int max_pw, double* __restrict__ Kcc, double* __restrict__ F) {
+    constexpr int NB = D + 1;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ __align__(8) unsigned long long bars[CC_TPB / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t strip_b = (size_t)max_w * 256, wbytes = 2 * strip_b + (size_t)max_pw * 384;
+    unsigned char* wbase = smraw + (size_t)warp * wbytes;
+    double* __restrict__ cc = (double*)wbase + lane;                         // [column*32]
+    double* __restrict__ acc = (double*)(wbase + strip_b) + lane;
+    const double* __restrict__ srv = (const double*)(wbase + 2 * strip_b) + lane;                               // [t*32]
+    const unsigned* __restrict__ spa = (const unsigned*)(wbase + 2 * strip_b + (size_t)max_pw * 256) + lane;    // [t*32]
+    const int S = blockIdx.x * (CC_TPB / 32) + warp;
+    if (S >= n_slices) return;
+    const int pw = pl_w[S];
+    const i64 po = pl_off[S];
+    if (lane == 0) {
+        mbar_init(&bars[warp], 1);
+        if (pw > 0) {
+            mbar_expect_tx(&bars[warp], (unsigned)pw * 384u);
+            bulk_g2s(wbase + 2 * strip_b, prv + po, (unsigned)pw * 256u, &bars[warp]);
+            bulk_g2s(wbase + 2 * strip_b + (size_t)max_pw * 256, ppa + po, (unsigned)pw * 128u, &bars[warp]);
+        }
+    }
+    __syncwarp();
+    const i64 base = slice_off[S] + lane;
+    const int w = slice_w[S];
+#pragma unroll 4
+    for (int j = 0; j < w; ++j) {
+        const int cidx = __ldg(&col[base + (i64)j * 32]);
+        cc[j * 32] = __ldg(&x[(i64)cidx * NB + D]);
+        acc[j * 32] = 0.0;
+    }
+    if (pw > 0) mbar_wait(&bars[warp], 0);
+#pragma unroll 2
+    for (int t = 0; t < pw; ++t) {
+        const double rv = srv[t * 32];
+        const unsigned ps = spa[t * 32];
+        const int a = (int)(ps >> 28);
+        int p[NB];
+        double cq[NB], av[NB], Ssum = 0.0, ca = 0.0;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            p[q] = (int)((ps >> (7 * q)) & 127u) * 32;
+            cq[q] = cc[p[q]];
+            av[q] = acc[p[q]];
+            Ssum += cq[q];
+            if (q == a) ca = cq[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+            acc[p[q]] = av[q] + rv * (q == a ? 4.0 * ca + 2.0 * Ssum : ca + cq[q] + Ssum);
+    }
+    const double kf = 2.0 * dt * Consts<D>::kappa;
+    double fc = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < w; ++j) {
+        const i64 s = base + (i64)j * 32;
+        const double kl = __ldcs(&Klin[s]);
+        const double jr = kf * acc[j * 32];
+        if (WK) __stcs(&Kcc[s], kl + jr);
+        fc += (kl + 0.5 * jr) * cc[j * 32];
+    }
+    const int r = S * 32 + lane;
+    if (F && r < n_rows) F[(i64)r * NB + D] = fc - mcp[r] - (fext ? fext[(i64)r * NB + D] : 0.0);
+}
+
 // F_u = K_uu u + K_uc c + lift - f_ext,u on vertex-blocked x; one thread per block row (as k_spmv_mono without the
 // concentration row).  xmask != null: multiply x by the Dirichlet mask first (used to compute the lift itself).
 template <int D>
@@ -447,13 +549,27 @@ void cc_mass_cprev(glims_ctx* c) {
 template <int D>
 static void cc_rows_dim(glims_ctx* c, CcMap* m, bool with_kcc, bool with_res) {
     const auto& p = c->pat;
-    const size_t smem = cc_smem(c);
     const int g = nblk(p.n_slices, CC_TPB / 32);
     const double* fext = c->have_load ? c->fext : nullptr;
+    const int mw = std::max(p.max_w, 1), mpw = std::max(m->max_pw, 4);
+    // bulk-copy variant when the per-warp stage (strips + whole list of the slice) leaves at least two CTAs per SM
+    const size_t smem_tma = (size_t)(CC_TPB / 32) * (2 * (size_t)mw * 256 + (size_t)mpw * 384);
+    static const bool no_tma = std::getenv("GLIMS_CC_NO_TMA") != nullptr;
+    if (!no_tma && smem_tma <= 100 * 1024) {
+#define CC_TMA(WK) do { auto kfn = k_cc_rows_tma<D, WK>; \
+        GL_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma)); \
+        kfn<<<g, CC_TPB, smem_tma, c->stream>>>(p.slice_off, p.slice_w, p.col, p.n_rows, p.n_slices, m->pl_off, m->pl_w, m->prv, \
+            m->ppa, m->Klin, m->mcp, fext, c->x, c->dt, mw, mpw, c->Kcc, with_res ? c->F : nullptr); } while (0)
+        if (with_kcc) CC_TMA(true); else CC_TMA(false);
+#undef CC_TMA
+        c->launches++;
+        return;
+    }
+    const size_t smem = cc_smem(c);
 #define CC_GO(WK) do { auto kfn = k_cc_rows<D, WK>; \
         GL_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kfn<<<g, CC_TPB, smem, c->stream>>>(p.slice_off, p.slice_w, p.col, p.n_rows, p.n_slices, m->pl_off, m->pl_w, m->prv, \
-            m->ppa, m->Klin, m->mcp, fext, c->x, c->dt, std::max(p.max_w, 1), c->Kcc, with_res ? c->F : nullptr); } while (0)
+            m->ppa, m->Klin, m->mcp, fext, c->x, c->dt, mw, c->Kcc, with_res ? c->F : nullptr); } while (0)
     if (with_kcc) CC_GO(true); else CC_GO(false);
 #undef CC_GO
     c->launches++;

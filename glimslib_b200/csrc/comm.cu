@@ -86,8 +86,8 @@ __device__ inline bool spin_until(const unsigned long long* flag, unsigned long 
 // One kernel per halo exchange.  Every CTA (1) gathers its share of my boundary values and stores them straight into
 // the neighbours' windows, (2) the CTA that finishes last publishes the sequence number to the neighbours, (3) every CTA
 // waits for the neighbours' sequence numbers and copies its share of the received values into the ghost block of x.
-// No CTA waits for another CTA of this grid (only for the neighbours, whose publication does not depend on mine), so the
-// kernel cannot deadlock even when the grid is larger than what is resident at once.
+// A rank's flag is published by the LAST of its CTAs to have pushed, and every CTA waits for the neighbours' flags: the
+// grid must therefore be co-resident (the launcher caps it with the occupancy API; the stream runs alone on the GPU).
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_halo(const P2PDev* __restrict__ P, T* __restrict__ x, const int* __restrict__ idx, long long n_send, int bs,
@@ -229,7 +229,18 @@ void exchange_p2p(glims_ctx* c, P2P* p, T* xb, int bs) {
     const i64 n_ghost = c->n_v - h.n_owned;
     if ((size_t)n_ghost * bs * sizeof(T) > (size_t)p->host.halo_bytes) throw GlError(GLIMS_ERR_ARG, "halo exchange: block too wide for the window");
     const i64 n = std::max(h.n_send, n_ghost) * bs;
-    int g = (int)std::min<i64>((n + 255) / 256, 148 * 2);
+    // every CTA waits for the neighbours' flags, and a rank publishes its flag only after ALL of its CTAs have pushed:
+    // the grid must be co-resident, or two ranks whose resident CTAs spin while the rest cannot start would wait for each
+    // other until the time-out.  Cap it with what the device can hold (occupancy API), not with a hard-coded SM count.
+    static int cap = 0;
+    if (cap == 0) {
+        int per_sm = 1, sms = 1, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_halo<T>, 256, 0);
+        cap = std::max(1, std::min(per_sm, 2) * sms);
+    }
+    int g = (int)std::min<i64>((n + 255) / 256, cap);
     k_halo<T><<<g > 0 ? g : 1, 256, 0, c->stream>>>(p->dev, xb, h.send_idx, h.n_send, bs, h.n_owned, n_ghost);
     c->launches++;
 }
@@ -465,7 +476,10 @@ void allgather_f32(glims_ctx* c, void* p, float* buf, i64 seg) {
     if (sb->p2p && h.p2p_enabled) {
         const size_t off = (size_t)((unsigned char*)buf - (sb->mine + SYM_DATA));
         const i64 total = (seg >> 2) * (h.n_ranks - 1);
-        int g = (int)std::min<i64>(std::max<i64>((total + 255) / 256, 1), 148);
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int g = (int)std::min<i64>(std::max<i64>((total + 255) / 256, 1), sms);      // co-resident (see k_halo)
         k_allgather32<<<g, 256, 0, c->stream>>>(sb->dev, off, seg);
         c->launches++;
         return;

@@ -19,11 +19,27 @@ class EngineError(RuntimeError):
 
 
 class Engine:
-    def __init__(self, coords, cells, cell_mat, device=0, n_owned=-1):
+    def __init__(self, coords, cells, cell_mat, device=0, n_owned=-1, reorder=None):
+        """``reorder='morton'`` (one GPU only): the library renumbers vertices and cells for locality before building its
+        sparsity pattern (``mesh.locality_order``) and installs the matching dof permutation, so that every host vector,
+        Dirichlet dof and derived field of this handle stays in the CALLER's numbering."""
         self._lib = N.load()
         coords = N.f64(coords)
         cells = np.ascontiguousarray(cells, dtype=np.int32)
         cell_mat = np.ascontiguousarray(cell_mat, dtype=np.int32)
+        self._new_of_old = self._cell_order = None
+        if reorder not in (None, "none", "morton"):
+            raise ValueError("reorder must be None or 'morton'")
+        if reorder == "morton":
+            if n_owned >= 0:
+                raise ValueError("reorder applies to an unpartitioned mesh (reorder before partitioning instead)")
+            from . import mesh as _mesh
+            self._new_of_old, self._cell_order = _mesh.locality_order(coords, cells)
+            old_of_new = np.empty_like(self._new_of_old)
+            old_of_new[self._new_of_old] = np.arange(len(coords))
+            coords = np.ascontiguousarray(coords[old_of_new])
+            cells = np.ascontiguousarray(self._new_of_old[cells][self._cell_order].astype(np.int32))
+            cell_mat = np.ascontiguousarray(cell_mat[self._cell_order])
         if coords.ndim != 2 or coords.shape[1] not in (2, 3):
             raise ValueError("coords must be (n_vertices, 2|3)")
         if cells.ndim != 2 or cells.shape[1] != coords.shape[1] + 1 or len(cell_mat) != len(cells):
@@ -44,6 +60,8 @@ class Engine:
         self.ndof = int(self._lib.glims_ndof(self._h))
         self.opts = N.SolverOpts()
         self._lib.glims_default_opts(C.byref(self.opts))
+        if self._new_of_old is not None:
+            self.set_dof_permutation((self._new_of_old[:, None] * self.nb + np.arange(self.nb)[None, :]).ravel())
 
     # -- plumbing -----------------------------------------------------------------------------
     def _check(self, rc, what):
@@ -203,6 +221,13 @@ class Engine:
         out = np.empty((n, nf))
         args = (None, N.as_dp(out)) if vertex else (N.as_dp(out), None)
         self._check(self._lib.glims_cell_fields(self._h, *args), "cell_fields")
+        if self._new_of_old is not None:          # back to the caller's vertex / cell order
+            if vertex:
+                out = out[self._new_of_old]
+            else:
+                inv = np.empty_like(self._cell_order)
+                inv[self._cell_order] = np.arange(len(inv))
+                out = out[inv]
         res = {"strain": out[:, :d * d].reshape(n, d, d), "stress": out[:, d * d:2 * d * d].reshape(n, d, d)}
         for k, name in enumerate(self.FIELD_NAMES[2:]):
             res[name] = out[:, 2 * d * d + k]

@@ -169,3 +169,53 @@ def voxel_ellipsoid_mesh(n, semi_axes):
     on_bnd = (cnt.ravel() > 0) & (cnt.ravel() < 8)
     mesh._boundary_vertices = new_id[np.nonzero(on_bnd)[0]]
     return mesh, r
+
+
+# ---- locality renumbering (the library's internal reorder; exposed through the dof-permutation API) ----------------------
+def _spread_bits(x, dim):
+    x = x.astype(np.uint64)
+    if dim == 3:        # 21 bits -> every third bit
+        x = (x | (x << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+        x = (x | (x << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x1249249249249249)
+    else:               # 32 bits -> every second bit
+        x = (x | (x << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x3333333333333333)
+        x = (x | (x << np.uint64(1))) & np.uint64(0x5555555555555555)
+    return x
+
+
+def morton_keys(coords):
+    d = coords.shape[1]
+    lo = coords.min(axis=0)
+    span = float((coords.max(axis=0) - lo).max()) or 1.0
+    bits = 21 if d == 3 else 31
+    q = np.minimum(((coords - lo) / span * (2 ** bits - 1)).astype(np.uint64), np.uint64(2 ** bits - 1))
+    key = np.zeros(len(coords), dtype=np.uint64)
+    for k in range(d):
+        key |= _spread_bits(q[:, k], d) << np.uint64(k)
+    return key
+
+
+def locality_order(coords, cells, window=1024):
+    """Vertex and cell order for meshes that arrive without locality: vertices along a Morton (Z-order) curve of their
+    coordinates, then -- inside windows of ``window`` consecutive vertices -- by descending vertex degree, so that the 32
+    rows of a SELL slice have similar lengths (SELL-C-sigma by renumbering); cells sorted by their smallest new vertex.
+    Returns (new_of_old[n_vertices], cell_order[n_cells])."""
+    coords, cells = np.asarray(coords), np.asarray(cells)
+    nv = len(coords)
+    order = np.argsort(morton_keys(coords), kind="stable")            # old id of new position
+    if window > 1:
+        deg = np.bincount(cells.ravel(), minlength=nv)                 # incident cells ~ row length
+        pos = np.arange(nv)
+        dmax = int(deg.max()) if nv else 0
+        key = (pos // window).astype(np.int64) * (dmax + 1) + (dmax - deg[order])
+        order = order[np.argsort(key, kind="stable")]
+    new_of_old = np.empty(nv, dtype=np.int64)
+    new_of_old[order] = np.arange(nv)
+    cmin = new_of_old[cells].min(axis=1)
+    return new_of_old, np.argsort(cmin, kind="stable")

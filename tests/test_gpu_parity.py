@@ -243,6 +243,68 @@ def test_time_dependent_dirichlet_values_keep_the_hierarchy(d):
     eng.close()
 
 
+@pytest.mark.parametrize("d", [2, 3])
+def test_dof_permutation_and_internal_reorder(d):
+    """glims_set_dof_permutation (SURVEY 8b `dof_permutation`): host vectors and Dirichlet dofs in an arbitrary caller
+    numbering -- here the UFC 'unreordered' mixed numbering DOLFIN uses with reorder_dofs_serial=False (component-major
+    blocks of vertex indices, data_io.py:242-252) -- give the same fields; and Engine(reorder='morton') renumbers the mesh
+    internally for locality while every result stays in the caller's numbering."""
+    from glimslib_b200.engine import Engine
+    prob, rng = small_problem(d, seed=31, n=8 if d == 3 else 20, jitter=0.2)
+    nb = d + 1
+    nv = len(prob.coords)
+    x0 = np.zeros(prob.ndof)
+    x0[nb - 1::nb] = np.exp(-8 * ((prob.coords - prob.coords.mean(axis=0)) ** 2).sum(axis=1))
+    kw = dict(snes_rtol=1e-11, snes_atol=1e-14, ksp_rtol=1e-12)
+    ref = make_engine(prob)
+    ref.set_prev(x0)
+    ref.set_state(np.zeros(prob.ndof))
+    ref.step(2, **kw)
+    x_ref = ref.get_state()
+    f_ref = ref.cell_fields()
+    fv_ref = ref.cell_fields(vertex=True)
+    ref.close()
+    # (a) component-major caller numbering: caller dof k*nv + v  <->  vertex-blocked v*nb + k
+    perm = (np.arange(nv)[None, :] * nb + np.arange(nb)[:, None]).ravel()
+    to_caller = lambda x: x.reshape(nv, nb).T.ravel()
+    eng = Engine(prob.coords, prob.cells, prob.cell_mat)
+    eng.set_dof_permutation(perm)
+    assert np.array_equal(eng.get_dof_permutation(), perm)
+    eng.set_materials(prob.mats.table())
+    eng.set_dt(prob.dt)
+    caller_bc = (prob.bc_dofs % nb) * nv + prob.bc_dofs // nb
+    eng.set_dirichlet(caller_bc, prob.bc_vals)
+    eng.set_load(to_caller(prob.f_ext))
+    eng.set_prev(to_caller(x0))
+    eng.set_state(np.zeros(prob.ndof))
+    eng.step(2, **kw)
+    assert np.abs(eng.get_state() - to_caller(x_ref)).max() <= 1e-12 * np.abs(x_ref).max()
+    eng.close()
+    # (b) internal Morton reorder on a randomly numbered copy of the mesh: results come back in the caller's numbering
+    pv = rng.permutation(nv)                  # new id of old vertex
+    inv = np.empty(nv, np.int64)
+    inv[pv] = np.arange(nv)
+    cperm = rng.permutation(len(prob.cells))
+    coords2 = np.ascontiguousarray(prob.coords[inv])
+    cells2 = np.ascontiguousarray(pv[prob.cells][cperm].astype(np.int32))
+    vec2 = lambda x: np.ascontiguousarray(x.reshape(nv, nb)[inv].ravel())
+    eng = Engine(coords2, cells2, prob.cell_mat[cperm], reorder="morton")
+    eng.set_materials(prob.mats.table())
+    eng.set_dt(prob.dt)
+    eng.set_dirichlet(pv[prob.bc_dofs // nb] * nb + prob.bc_dofs % nb, prob.bc_vals)
+    eng.set_load(vec2(prob.f_ext))
+    eng.set_prev(vec2(x0))
+    eng.set_state(np.zeros(prob.ndof))
+    eng.step(2, **kw)
+    x2 = eng.get_state()
+    assert np.abs(x2 - vec2(x_ref)).max() <= 1e-9 * np.abs(x_ref).max()
+    f2 = eng.cell_fields()
+    assert np.abs(f2["von_mises"] - f_ref["von_mises"][cperm]).max() <= 1e-8 * np.abs(f_ref["von_mises"]).max()
+    fv2 = eng.cell_fields(vertex=True)
+    assert np.abs(fv2["pressure"] - fv_ref["pressure"][inv]).max() <= 1e-8 * np.abs(fv_ref["pressure"]).max()
+    eng.close()
+
+
 @pytest.mark.parametrize("config", ["c1", "c3_small"])
 def test_default_tolerances_meet_the_parity_bar(config):
     """The tolerances bench.py times (glims_default_opts: SNES rtol 1e-9 / atol 1e-10, KSP rtol 1e-10) against the oracle
