@@ -18,6 +18,7 @@
 #include <cmath>
 #include <numeric>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <functional>
 
@@ -286,6 +287,28 @@ __global__ void k_block_diag_inverse(const int* __restrict__ diag, int n, const 
     for (int i = 0; i < BS; ++i) for (int j = 0; j < BS; ++j) out[(i64)r * BS * BS + i * BS + j] = inv[i][j];
 }
 
+// In-place Gauss-Jordan inverse of a (regularised) SPD matrix on the device: M (m x m, row major) is reduced to the
+// identity while Inv (identity on entry) becomes its inverse.  SPD => no pivoting.  Two small kernels per pivot (scale the
+// pivot row + save the pivot column; rank-one update of both halves with a full grid): ~10 us per pivot.  Only used for
+// the coarsest level when it is too large for the host loop (m up to ~1500).
+__global__ void k_gj_pivot(double* M, double* Inv, int m, int p, double* fcol) {
+    __shared__ double ip;
+    if (threadIdx.x == 0) ip = 1.0 / M[(i64)p * m + p];
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) fcol[i] = (i == p) ? 0.0 : M[(i64)i * m + p];
+    for (int j = threadIdx.x; j < m; j += blockDim.x) { M[(i64)p * m + j] *= ip; Inv[(i64)p * m + j] *= ip; }
+}
+__global__ void k_gj_update(double* M, double* Inv, int m, int p, const double* __restrict__ fcol) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;       // column of [M | Inv]
+    const int i = blockIdx.y;                                  // row
+    if (j >= 2 * m) return;
+    const double f = fcol[i];
+    if (f == 0.0) return;
+    double* T = j < m ? M : Inv;
+    const int jj = j < m ? j : j - m;
+    T[(i64)i * m + jj] -= f * T[(i64)p * m + jj];
+}
+
 __global__ void k_dense_matvec(const double* __restrict__ M, const double* __restrict__ x, double* __restrict__ y, int m) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -518,23 +541,18 @@ template <int BS, typename MT>
 __device__ inline float split_row_dot(const i64 base, const int w, const int* __restrict__ col, const MT* __restrict__ A,
                                       const float* __restrict__ x, const int i, const int lane) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int j = 0;
-    for (; j + 3 < w; j += 4) {
+    // whole rounds of four: columns past the slice width are clamped to the last one and weighted by zero (no serial tail)
+    for (int j = 0; j < w; j += 4) {
         int cc[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) cc[u] = __ldg(&col[base + (i64)(j + u) * 32 + lane]);
+        for (int u = 0; u < 4; ++u) cc[u] = __ldg(&col[base + (i64)min(j + u, w - 1) * 32 + lane]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const MT* Au = A + (base + (i64)(j + u) * 32) * (BS * BS) + (i * BS) * 32 + lane;
+            const MT* Au = A + (base + (i64)min(j + u, w - 1) * 32) * (BS * BS) + (i * BS) * 32 + lane;
+            const float on = (j + u < w) ? 1.f : 0.f;
 #pragma unroll
-            for (int b = 0; b < BS; ++b) acc[u] += ld_mat(&Au[b * 32]) * __ldg(&x[(i64)cc[u] * BS + b]);
+            for (int b = 0; b < BS; ++b) acc[u] += on * ld_mat(&Au[b * 32]) * __ldg(&x[(i64)cc[u] * BS + b]);
         }
-    }
-    for (; j < w; ++j) {
-        const int c0 = __ldg(&col[base + (i64)j * 32 + lane]);
-        const MT* A0 = A + (base + (i64)j * 32) * (BS * BS) + (i * BS) * 32 + lane;
-#pragma unroll
-        for (int b = 0; b < BS; ++b) acc[0] += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
     }
     return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
@@ -973,6 +991,10 @@ void amg_free(glims_ctx* c) {
 }
 
 void amg_setup(glims_ctx* c) {
+    const bool verbose_t = std::getenv("GLIMS_VERBOSE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_levels = 0, t_dense = 0, t_lmax = 0;
     amg_free(c);
     Amg* amg = new Amg();
     c->amg = amg;
@@ -1010,7 +1032,9 @@ void amg_setup(glims_ctx* c) {
         alloc_work(l);
         diag_inverse(c, l, level == 0 ? 0.0 : 1e-8);
         const int n = l.n;
-        const bool last = ((n * l.bs <= 600) && !(dist && level == 0)) || level >= 12;
+        // coarsest level = dense inverse: up to ~256 nodes (one matrix-vector product instead of another smoothed level:
+        // every level costs seven latency-bound phases per V-cycle)
+        const bool last = ((n * l.bs <= 1536) && !(dist && level == 0)) || level >= 12;
         if (last) break;
         // ---- aggregation on the host ---------------------------------------------------------------
         HostGraph g = download_graph(l.pat);
@@ -1163,6 +1187,7 @@ void amg_setup(glims_ctx* c) {
         Xl.swap(Xc);
         ++level;
     }
+    t_levels = now();
     // ---- coarsest level: dense (regularised) inverse on the host --------------------------------------
     {
         Level& l = amg->L.back();
@@ -1190,6 +1215,21 @@ void amg_setup(glims_ctx* c) {
             M[(i64)i * m + i] += 1e-10 * dmax;                          // floating sub-domains: regularise the rigid modes
             Inv[(i64)i * m + i] = 1.0;
         }
+        GL_CUDA(cudaMalloc(&amg->coarse_inv, sizeof(double) * std::max<i64>((i64)m * m, 1)));
+        if (m > 600) {
+            // large coarsest level: invert on the device (the O(m^3) host loop would take seconds)
+            double *dM = nullptr, *df = nullptr;
+            GL_CUDA(cudaMalloc(&dM, sizeof(double) * (i64)m * m));
+            GL_CUDA(cudaMalloc(&df, sizeof(double) * m));
+            GL_CUDA(cudaMemcpy(dM, M.data(), sizeof(double) * (i64)m * m, cudaMemcpyHostToDevice));
+            GL_CUDA(cudaMemcpy(amg->coarse_inv, Inv.data(), sizeof(double) * (i64)m * m, cudaMemcpyHostToDevice));
+            for (int p = 0; p < m; ++p) {
+                k_gj_pivot<<<1, 1024, 0, c->stream>>>(dM, amg->coarse_inv, m, p, df);
+                k_gj_update<<<dim3((2 * m + 255) / 256, m), 256, 0, c->stream>>>(dM, amg->coarse_inv, m, p, df);
+            }
+            GL_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(dM); cudaFree(df);
+        } else {
         for (int p = 0; p < m; ++p) {
             int piv = p; double best = std::fabs(M[(i64)p * m + p]);
             for (int i = p + 1; i < m; ++i) if (std::fabs(M[(i64)i * m + p]) > best) { best = std::fabs(M[(i64)i * m + p]); piv = i; }
@@ -1203,9 +1243,10 @@ void amg_setup(glims_ctx* c) {
                 for (int j = 0; j < m; ++j) { M[(i64)i * m + j] -= f * M[(i64)p * m + j]; Inv[(i64)i * m + j] -= f * Inv[(i64)p * m + j]; }
             }
         }
-        GL_CUDA(cudaMalloc(&amg->coarse_inv, sizeof(double) * std::max<i64>((i64)m * m, 1)));
         GL_CUDA(cudaMemcpy(amg->coarse_inv, Inv.data(), sizeof(double) * (i64)m * m, cudaMemcpyHostToDevice));
+        }
     }
+    t_dense = now();
     // ---- smoother spectra ----------------------------------------------------------------------------
     for (size_t li = 0; li + 1 < amg->L.size(); ++li) estimate_lmax(c, amg->L[li]);
     GL_CUDA(cudaStreamSynchronize(c->stream));
@@ -1217,7 +1258,9 @@ void amg_setup(glims_ctx* c) {
         comm_allreduce_max_f64(c, lm.data(), (int)lm.size());
         for (size_t li = 0; li < amg->L.size(); ++li) amg->L[li].lmax = lm[li];
     }
+    t_lmax = now();
     build_fp32(c, amg);
+    if (verbose_t) fprintf(stderr, "glims amg setup: levels %.3f s, coarsest inverse %.3f s, spectra %.3f s, fp32 copies %.3f s\n", t_levels - t_begin, t_dense - t_levels, t_lmax - t_dense, now() - t_lmax);
     if (std::getenv("GLIMS_VERBOSE"))
         for (size_t li = 0; li < amg->L.size(); ++li) {
             const Level& l = amg->L[li];

@@ -42,18 +42,19 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
 __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// all CTAs of the (co-resident) grid; sense-reversing: leaves the arrival counter at zero.  The wait is bounded (about two
-// seconds of SM clock): a grid that is not co-resident after all raises bar[2] (amg_fused_check) instead of hanging the GPU.
-__device__ __forceinline__ void fused_grid_barrier(unsigned* bar) {
+// all CTAs of the (co-resident) grid; sense-reversing: leaves the arrival counter at zero.  `gen` is the generation this CTA
+// expects (read once at kernel start, then tracked in a register: one L2 round trip less per barrier); the arrival is a
+// release-atomic, the wait an acquire-load.  The wait is bounded (about two seconds of SM clock): a grid that is not
+// co-resident after all raises bar[2] (amg_fused_failed) instead of hanging the GPU.
+__device__ __forceinline__ void fused_grid_barrier(unsigned* bar, unsigned& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned gen = ld_acquire_gpu_u32(bar + 1);
-        __threadfence();
-        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+        unsigned prev;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+        if (prev == gridDim.x - 1) {
             bar[0] = 0u;
-            __threadfence();
             st_release_gpu_u32(bar + 1, gen + 1u);
-        } else if (ld_acquire_gpu_u32(bar + 2) == 0u) {
+        } else {
             const long long t0 = clock64();
             while (ld_acquire_gpu_u32(bar + 1) == gen) {
                 if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 2, 1u); break; }
@@ -61,64 +62,82 @@ __device__ __forceinline__ void fused_grid_barrier(unsigned* bar) {
         }
         __threadfence();
     }
+    gen += 1u;
     __syncthreads();
 }
 
-// component i of (A x) for row `lane` of a slice; x through L2.  Eight block columns in flight: a row of ~24 blocks is
-// three rounds of dependent loads (column index -> x), which is what a phase costs on these latency-bound levels.
+// Vectors written by other CTAs in an earlier phase: a plain (L1-cached) load is safe because the grid barrier's acquire
+// (thread 0: ld.acquire.gpu + fence => CCTL.IVALL, then bar.sync) invalidates the SM's L1 -- the cooperative-groups
+// grid.sync discipline.  Going through L1 matters: the six component warps of a slice and neighbouring rows gather the
+// same x blocks, and with L2-only loads (ld.cg) the ~90 KB vector became an L2 hot spot (3 M sector requests per phase).
+template <typename T> __device__ __forceinline__ T vload(const T* p) { return *p; }
+constexpr int FUSED_CG = 4;      // column groups per block-row component: a slice's columns are split over CG warps
+constexpr int FUSED_U = 6;       // block columns a warp holds in flight per round
+
+// partial sum of component i of (A x) for row `lane` of a slice over the columns g*U + u + k*CG*U; x through L2.
+// One round covers CG*U = 24 columns, i.e. a whole row of these levels: two dependent load latencies (column -> x).
 template <int BS>
 __device__ __forceinline__ float fused_row_dot(const i64 base, const int w, const int* __restrict__ col,
-                                               const float* __restrict__ A, const float* x, const int i, const int lane) {
-    constexpr int U = 8;
-    float acc[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) acc[u] = 0.f;
-    int j = 0;
-    for (; j + U - 1 < w; j += U) {
+                                               const float* __restrict__ A, const float* x, const int i, const int g,
+                                               const int lane, int* scol /* this warp's [U][32] staging area */) {
+    constexpr int U = FUSED_U;
+    float s = 0.f;
+    for (int j0 = g * U; j0 < w; j0 += FUSED_CG * U) {
         int cc[U];
-        float av[U][BS];
+        float av[U][BS], xv[U][BS];
 #pragma unroll
-        for (int u = 0; u < U; ++u) cc[u] = __ldg(&col[base + (i64)(j + u) * 32 + lane]);
+        for (int u = 0; u < U; ++u) cc[u] = __ldg(&col[base + (i64)min(j0 + u, w - 1) * 32 + lane]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float* Au = A + (base + (i64)(j + u) * 32) * (BS * BS) + (i * BS) * 32 + lane;
+            const float* Au = A + (base + (i64)min(j0 + u, w - 1) * 32) * (BS * BS) + (i * BS) * 32 + lane;
 #pragma unroll
             for (int b = 0; b < BS; ++b) av[u][b] = __ldg(&Au[b * 32]);
         }
+        // A warp issues in order and the x loads depend on the column indices.  Left alone, the scheduler interleaves
+        // "column u, x of column u" and the chain becomes U load latencies long.  Passing the indices through shared
+        // memory around a warp barrier pins the order: all U column loads first, then all x loads -- two latencies.
+#pragma unroll
+        for (int u = 0; u < U; ++u) scol[u * 32 + lane] = cc[u];
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < U; ++u) cc[u] = scol[u * 32 + lane];
+        __syncwarp();
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int b = 0; b < BS; ++b) acc[u] += av[u][b] * __ldcg(&x[(i64)cc[u] * BS + b]);
-    }
-    for (; j < w; ++j) {
-        const int c0 = __ldg(&col[base + (i64)j * 32 + lane]);
-        const float* A0 = A + (base + (i64)j * 32) * (BS * BS) + (i * BS) * 32 + lane;
+            for (int b = 0; b < BS; ++b) xv[u][b] = vload(&x[(i64)cc[u] * BS + b]);
 #pragma unroll
-        for (int b = 0; b < BS; ++b) acc[j & (U - 1)] += __ldg(&A0[b * 32]) * __ldcg(&x[(i64)c0 * BS + b]);
-    }
-    float s = 0.f;
+        for (int u = 0; u < U; ++u) {
+            const float on = (j0 + u < w) ? 1.f : 0.f;
 #pragma unroll
-    for (int u = 0; u < U; ++u) s += acc[u];
+            for (int b = 0; b < BS; ++b) s += on * av[u][b] * xv[u][b];
+        }
+    }
     return s;
 }
 
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// The plan travels as a kernel parameter (constant bank): phase and level descriptors cost no global-memory round trip.
 template <int D>
-__global__ void __launch_bounds__(32 * ((D == 2) ? 3 : 6))
-k_amg_fused(const FusedPlan* __restrict__ plan) {
-    constexpr int BS = (D == 2) ? 3 : 6, NT = 32 * BS;
+__global__ void __launch_bounds__(32 * ((D == 2) ? 3 : 6) * FUSED_CG)
+k_amg_fused(const __grid_constant__ FusedPlan plan) {
+    constexpr int BS = (D == 2) ? 3 : 6, NW = BS * FUSED_CG, NT = 32 * NW;
+    __shared__ float part[FUSED_CG][BS][32];
+    __shared__ int scol_all[NW][FUSED_U * 32];
     __shared__ float rs[BS][32];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int ci = wi % BS, cg = wi / BS;                 // component / column group of this warp in the matrix phases
     const int gtid = blockIdx.x * NT + threadIdx.x, gthreads = gridDim.x * NT;
-    const int gwarp = blockIdx.x * BS + wi, gwarps = gridDim.x * BS;
-    const int n_phases = plan->n_phases;
-    if (gtid == 0) plan->tstamp[0] = global_ns();
+    const int gwarp = blockIdx.x * NW + wi, gwarps = gridDim.x * NW;
+    const int n_phases = plan.n_phases;
+    unsigned bar_gen = ld_acquire_gpu_u32(plan.bar + 1);
+    if (gtid == 0) plan.tstamp[0] = global_ns();
     // The matrices of these levels were evicted from L2 by the fine-level streams of the same PCG iteration and every
     // phase is a chain of dependent loads: pull them (and the transfer maps) back into L2 while phase 0 runs.
-    for (int k = 1; k + 1 < plan->n_levels; ++k) {
-        const FusedLevel& F = plan->L[k];
+    for (int k = 1; k + 1 < plan.n_levels; ++k) {
+        const FusedLevel& F = plan.L[k];
         const i64 n_slots = F.slice_off[F.n_slices];
         const char* a = (const char*)F.A;
         const i64 nb_a = n_slots * (i64)(BS * BS) * 4, nb_c = n_slots * 4, nb_d = (i64)F.n * BS * BS * 4;
@@ -126,12 +145,16 @@ k_amg_fused(const FusedPlan* __restrict__ plan) {
         for (i64 o = (i64)gtid * 128; o < nb_c; o += (i64)gthreads * 128) prefetch_l2((const char*)F.col + o);
         for (i64 o = (i64)gtid * 128; o < nb_d; o += (i64)gthreads * 128) prefetch_l2((const char*)F.dinv + o);
     }
+    if (plan.coarse_m > 0) {
+        const i64 nb_i = (i64)plan.coarse_m * plan.coarse_m * 4;
+        for (i64 o = (i64)gtid * 128; o < nb_i; o += (i64)gthreads * 128) prefetch_l2((const char*)plan.coarse_inv + o);
+    }
     for (int ph = 0; ph < n_phases; ++ph) {
-        const FusedPhase P = plan->P[ph];
-        const FusedLevel& L = plan->L[P.lvl];
+        const FusedPhase& P = plan.P[ph];
+        const FusedLevel& L = plan.L[P.lvl];
         if (P.op == FOP_RESTRICT) {
             // b(next) = P^T r: one warp per aggregate, lanes over its members, shuffle reduction (as k_restrict32)
-            const FusedLevel& C = plan->L[P.lvl + 1];
+            const FusedLevel& C = plan.L[P.lvl + 1];
             for (int I = gwarp; I < L.nc; I += gwarps) {
                 double acc[6] = {0, 0, 0, 0, 0, 0};
                 for (int m = L.mem_ptr[I] + lane; m < L.mem_ptr[I + 1]; m += 32) {
@@ -139,8 +162,10 @@ k_amg_fused(const FusedPlan* __restrict__ plan) {
                     double Pm[6][6];
                     int a_, b_;
                     build_P<D>(false, L.rvec + (i64)i * D, 0xffu, Pm, a_, b_);
+#pragma unroll
                     for (int k = 0; k < BS; ++k) {
-                        const double v = __ldcg(&P.src[(i64)i * BS + k]);
+                        const double v = vload(&P.src[(i64)i * BS + k]);
+#pragma unroll
                         for (int j = 0; j < BS; ++j) acc[j] += Pm[k][j] * v;
                     }
                 }
@@ -158,7 +183,7 @@ k_amg_fused(const FusedPlan* __restrict__ plan) {
                 const int row = t / BS, i = t - row * BS;
                 float z = 0.f;
 #pragma unroll
-                for (int j = 0; j < BS; ++j) z += __ldg(&L.dinv[(i64)row * BS * BS + i * BS + j]) * __ldcg(&L.b[(i64)row * BS + j]);
+                for (int j = 0; j < BS; ++j) z += __ldg(&L.dinv[(i64)row * BS * BS + i * BS + j]) * vload(&L.b[(i64)row * BS + j]);
                 const float dn = P.c2 * z;
                 L.d[t] = dn;
                 P.dst[t] = dn;
@@ -168,60 +193,89 @@ k_amg_fused(const FusedPlan* __restrict__ plan) {
                 const int r = S * 32 + lane;
                 const i64 base = L.slice_off[S];
                 const int w = L.slice_w[S];
-                const float dotv = fused_row_dot<BS>(base, w, L.col, L.A, P.src, wi, lane);
-                const float res = r < L.n ? __ldcg(&L.b[(i64)r * BS + wi]) - dotv : 0.f;
-                if (P.op == FOP_RESID) {
-                    if (r < L.n) L.r[(i64)r * BS + wi] = res;
-                } else {
-                    rs[wi][lane] = res;
+                // issue the row-local loads before the column walk: they overlap its two latencies
+                float bv = 0.f, dv = 0.f, xo = 0.f, dinv_row[BS];
+                if (cg == 0 && r < L.n) {
+                    bv = vload(&L.b[(i64)r * BS + ci]);
+                    if (P.op == FOP_STEP) {
+                        dv = P.c1 != 0.f ? vload(&L.d[(i64)r * BS + ci]) : 0.f;
+                        xo = vload(&P.src[(i64)r * BS + ci]);
+#pragma unroll
+                        for (int jj = 0; jj < BS; ++jj) dinv_row[jj] = __ldg(&L.dinv[(i64)r * BS * BS + ci * BS + jj]);
+                    }
+                }
+                if (gtid == 0) plan.tstamp[128 + ph * 4 + 0] = global_ns();
+                part[cg][ci][lane] = fused_row_dot<BS>(base, w, L.col, L.A, P.src, ci, cg, lane, scol_all[wi]);
+                if (gtid == 0) plan.tstamp[128 + ph * 4 + 1] = global_ns();
+                __syncthreads();
+                if (gtid == 0) plan.tstamp[128 + ph * 4 + 2] = global_ns();
+                if (cg == 0) {
+                    float dotv = part[0][ci][lane];
+#pragma unroll
+                    for (int q = 1; q < FUSED_CG; ++q) dotv += part[q][ci][lane];
+                    const float res = r < L.n ? bv - dotv : 0.f;
+                    if (P.op == FOP_RESID) {
+                        if (r < L.n) L.r[(i64)r * BS + ci] = res;
+                    } else rs[ci][lane] = res;
+                }
+                if (P.op == FOP_STEP) {
                     __syncthreads();
-                    if (r < L.n) {
+                    if (cg == 0 && r < L.n) {
                         float z = 0.f;
 #pragma unroll
-                        for (int jj = 0; jj < BS; ++jj) z += __ldg(&L.dinv[(i64)r * BS * BS + wi * BS + jj]) * rs[jj][lane];
-                        const float dn = P.c2 * z + (P.c1 != 0.f ? P.c1 * __ldcg(&L.d[(i64)r * BS + wi]) : 0.f);
-                        L.d[(i64)r * BS + wi] = dn;
-                        P.dst[(i64)r * BS + wi] = __ldcg(&P.src[(i64)r * BS + wi]) + dn;
+                        for (int jj = 0; jj < BS; ++jj) z += dinv_row[jj] * rs[jj][lane];
+                        const float dn = P.c2 * z + P.c1 * dv;
+                        L.d[(i64)r * BS + ci] = dn;
+                        P.dst[(i64)r * BS + ci] = xo + dn;
                     }
-                    __syncthreads();
                 }
+                __syncthreads();
             }
         } else if (P.op == FOP_DENSE) {
-            const int m = plan->coarse_m;
+            const int m = plan.coarse_m;
             for (int row = gwarp; row < m; row += gwarps) {
                 float s = 0.f;
-                for (int j = lane; j < m; j += 32) s += __ldg(&plan->coarse_inv[(i64)row * m + j]) * __ldcg(&L.b[j]);
+                for (int j = lane; j < m; j += 32) s += __ldg(&plan.coarse_inv[(i64)row * m + j]) * vload(&L.b[j]);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane == 0) L.x[row] = s;
             }
         } else if (P.op == FOP_PROLONG) {
             // dst(level) += P x(next)
-            const FusedLevel& C = plan->L[P.lvl + 1];
+            const FusedLevel& C = plan.L[P.lvl + 1];
             for (int i = gtid; i < L.n; i += gthreads) {
                 const int I = L.agg[i];
                 if (I < 0) continue;
                 double Pm[6][6];
                 int a_, b_;
                 build_P<D>(false, L.rvec + (i64)i * D, 0xffu, Pm, a_, b_);
+                double xc[BS];
+#pragma unroll
+                for (int j = 0; j < BS; ++j) xc[j] = (double)vload(&C.x[(i64)I * BS + j]);
+#pragma unroll
                 for (int k = 0; k < BS; ++k) {
                     double v = 0;
-                    for (int j = 0; j < BS; ++j) v += Pm[k][j] * (double)__ldcg(&C.x[(i64)I * BS + j]);
-                    P.dst[(i64)i * BS + k] = __ldcg(&P.dst[(i64)i * BS + k]) + (float)v;
+#pragma unroll
+                    for (int j = 0; j < BS; ++j) v += Pm[k][j] * xc[j];
+                    P.dst[(i64)i * BS + k] = vload(&P.dst[(i64)i * BS + k]) + (float)v;
                 }
             }
         } else if (P.op == FOP_COPY) {
-            for (int t = gtid; t < L.n * BS; t += gthreads) P.dst[t] = __ldcg(&P.src[t]);
+            for (int t = gtid; t < L.n * BS; t += gthreads) P.dst[t] = vload(&P.src[t]);
         }
-        if (ph + 1 < n_phases) fused_grid_barrier(plan->bar);
-        if (gtid == 0) plan->tstamp[ph + 1] = global_ns();
+        if (gtid == 0) plan.tstamp[128 + ph * 4 + 3] = global_ns();
+        if (ph == 2 && threadIdx.x == 0 && blockIdx.x < 512) { plan.tstamp[1024 + blockIdx.x] = global_ns(); unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); plan.tstamp[1536 + blockIdx.x] = sm; }
+        if (ph + 1 < n_phases) fused_grid_barrier(plan.bar, bar_gen);
+        if (gtid == 0) plan.tstamp[ph + 1] = global_ns();
     }
 }
 
 struct FusedHost {
-    FusedPlan* dev = nullptr;
+    FusedPlan* plan = nullptr;      // host copy: passed to the kernel by value (__grid_constant__)
     unsigned* bar = nullptr;
     unsigned long long* tstamp = nullptr;
+    void* arena = nullptr;          // one allocation holding every matrix, map and vector of the fused levels
+    size_t arena_bytes = 0;
     std::vector<int> ops, lvls;
     int grid = 0, top_level = 0;
     float* top_cur = nullptr;       // the iterate buffer of the level above that the plan prolongs into
@@ -231,9 +285,10 @@ struct FusedHost {
 static void amg_fused_free(Amg* amg) {
     FusedHost* f = (FusedHost*)amg->fused;
     if (!f) return;
-    if (f->dev) cudaFree(f->dev);
+    if (f->plan) delete f->plan;
     if (f->bar) cudaFree(f->bar);
     if (f->tstamp) cudaFree(f->tstamp);
+    if (f->arena) cudaFree(f->arena);
     delete f;
     amg->fused = nullptr;
 }
@@ -247,17 +302,75 @@ static FusedHost* amg_fused_build(glims_ctx* c, Amg* amg, int top, float* cur) {
     memset(P, 0, sizeof(FusedPlan));
     P->n_levels = nl - top;
     if (P->n_levels > FUSED_MAX_LEVELS) { delete P; return f; }
+    // Everything the kernel reads or writes (except r32 / cur of the level above) lives in ONE allocation: the data of
+    // these levels are ~20 MB, but spread over fifty separate allocations they cost fifty 2 MB pages, and after the
+    // fine-level kernels of an iteration have streamed gigabytes through the TLBs every phase started with a storm of
+    // page walks (measured: the slowest CTA of a matrix phase took 22 us for 5 us of work).
+    std::vector<i64> h_so;      // slot counts
+    size_t arena_bytes = 0;
+    auto reserve = [&](size_t b) { size_t o = arena_bytes; arena_bytes += (b + 255) & ~(size_t)255; return o; };
+    struct Off { size_t so, sw, col, A, dinv, x, y, b, r, d, agg, rvec, mptr, midx; i64 n_slots; int n_mem; };
+    std::vector<Off> offs(P->n_levels);
+    for (int k = 0; k < P->n_levels; ++k) {
+        const Level& l = amg->L[top + k];
+        Off& o = offs[k];
+        o.n_slots = l.pat.n_slots;
+        const i64 bb = (i64)l.bs * l.bs, nv = (i64)l.n * l.bs;
+        const bool last = (k + 1 == P->n_levels);
+        if (k > 0 && !last && !l.A32) { delete P; return f; }      // FP16 coarse levels: not fused
+        if (k > 0) {
+            if (!last) {
+                o.so = reserve(sizeof(i64) * (l.pat.n_slices + 1)); o.sw = reserve(sizeof(int) * l.pat.n_slices);
+                o.col = reserve(sizeof(int) * o.n_slots); o.A = reserve(sizeof(float) * o.n_slots * bb);
+                o.dinv = reserve(sizeof(float) * l.n * bb);
+            }
+            o.x = reserve(4 * nv); o.y = reserve(4 * nv); o.b = reserve(4 * nv); o.r = reserve(4 * nv); o.d = reserve(4 * nv);
+        }
+        if (!last) {
+            GL_CUDA(cudaMemcpy(&o.n_mem, l.mem_ptr + l.nc_local, sizeof(int), cudaMemcpyDeviceToHost));
+            o.agg = reserve(sizeof(int) * l.n); o.rvec = reserve(sizeof(double) * (i64)l.n * amg->dim);
+            o.mptr = reserve(sizeof(int) * (l.nc_local + 1)); o.midx = reserve(sizeof(int) * std::max(o.n_mem, 1));
+        }
+    }
+    const size_t o_inv = reserve(sizeof(float) * (size_t)amg->coarse_m * amg->coarse_m);
+    GL_CUDA(cudaMalloc(&f->arena, arena_bytes));
+    GL_CUDA(cudaMemset(f->arena, 0, arena_bytes));
+    unsigned char* ar = (unsigned char*)f->arena;
+    auto put = [&](size_t off, const void* src, size_t bytes) {
+        if (bytes) GL_CUDA(cudaMemcpy(ar + off, src, bytes, cudaMemcpyDeviceToDevice));
+        return (void*)(ar + off);
+    };
     for (int k = 0; k < P->n_levels; ++k) {
         const Level& l = amg->L[top + k];
         FusedLevel& F = P->L[k];
+        const Off& o = offs[k];
+        const i64 bb = (i64)l.bs * l.bs;
+        const bool last = (k + 1 == P->n_levels);
         F.n = l.n; F.n_slices = l.pat.n_slices; F.bs = l.bs;
-        F.slice_off = l.pat.slice_off; F.slice_w = l.pat.slice_w; F.col = l.pat.col;
-        F.A = l.A32; F.dinv = l.dinv32;
-        F.x = l.x32; F.y = l.y32; F.b = l.b32; F.r = l.r32; F.d = l.d32;
-        F.nc = l.nc; F.mem_ptr = l.mem_ptr; F.mem_idx = l.mem_idx; F.agg = l.agg; F.rvec = l.rvec;
-        if (k > 0 && k + 1 < P->n_levels && !l.A32) { delete P; return f; }      // FP16 coarse levels: not fused
+        F.nc = l.nc;
+        if (k == 0) {
+            // level above the fused block: only its r32 (read by the first restriction) and the transfer maps are used
+            F.r = l.r32;
+        } else {
+            if (!last) {
+                F.slice_off = (const i64*)put(o.so, l.pat.slice_off, sizeof(i64) * (l.pat.n_slices + 1));
+                F.slice_w = (const int*)put(o.sw, l.pat.slice_w, sizeof(int) * l.pat.n_slices);
+                F.col = (const int*)put(o.col, l.pat.col, sizeof(int) * o.n_slots);
+                F.A = (const float*)put(o.A, l.A32, sizeof(float) * o.n_slots * bb);
+                F.dinv = (const float*)put(o.dinv, l.dinv32, sizeof(float) * l.n * bb);
+            }
+            F.x = (float*)(ar + o.x); F.y = (float*)(ar + o.y); F.b = (float*)(ar + o.b); F.r = (float*)(ar + o.r); F.d = (float*)(ar + o.d);
+        }
+        if (!last) {
+            F.agg = (const int*)put(o.agg, l.agg, sizeof(int) * l.n);
+            F.rvec = (const double*)put(o.rvec, l.rvec, sizeof(double) * (i64)l.n * amg->dim);
+            F.mem_ptr = (const int*)put(o.mptr, l.mem_ptr, sizeof(int) * (l.nc_local + 1));
+            F.mem_idx = (const int*)put(o.midx, l.mem_idx, sizeof(int) * o.n_mem);
+        }
     }
-    P->coarse_m = amg->coarse_m; P->coarse_inv = amg->coarse_inv32;
+    P->coarse_inv = (const float*)put(o_inv, amg->coarse_inv32, sizeof(float) * (size_t)amg->coarse_m * amg->coarse_m);
+    f->arena_bytes = arena_bytes;
+    P->coarse_m = amg->coarse_m;
     int np = 0;
     bool ok = true;
     auto push = [&](int op, int lvl, float* src, float* dst, double c1, double c2) {
@@ -296,26 +409,24 @@ static FusedHost* amg_fused_build(glims_ctx* c, Amg* amg, int top, float* cur) {
     GL_CUDA(cudaMalloc(&f->bar, 4 * sizeof(unsigned)));
     GL_CUDA(cudaMemset(f->bar, 0, 4 * sizeof(unsigned)));
     P->bar = f->bar;
-    GL_CUDA(cudaMalloc(&f->tstamp, (FUSED_MAX_PHASES + 1) * sizeof(unsigned long long)));
-    GL_CUDA(cudaMemset(f->tstamp, 0, (FUSED_MAX_PHASES + 1) * sizeof(unsigned long long)));
+    GL_CUDA(cudaMalloc(&f->tstamp, 2048 * sizeof(unsigned long long)));
+    GL_CUDA(cudaMemset(f->tstamp, 0, 2048 * sizeof(unsigned long long)));
     P->tstamp = f->tstamp;
     for (int i = 0; i < np; ++i) { f->ops.push_back(P->P[i].op); f->lvls.push_back(P->P[i].lvl); }
-    GL_CUDA(cudaMalloc(&f->dev, sizeof(FusedPlan)));
-    GL_CUDA(cudaMemcpy(f->dev, P, sizeof(FusedPlan), cudaMemcpyHostToDevice));
     // grid: enough CTAs for the widest phase, never more than can be co-resident (the barrier spins)
-    const int D = amg->dim, NT = 32 * (D == 2 ? 3 : 6);
+    const int D = amg->dim, NT = 32 * (D == 2 ? 3 : 6) * FUSED_CG;
     int per_sm = 0, sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (D == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_amg_fused<2>, NT, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_amg_fused<3>, NT, 0);
-    int want = std::max(P->L[1].n_slices, (P->L[0].n + NT * 4 - 1) / (NT * 4));
+    int want = std::max(P->L[1].n_slices, (P->L[0].n + NT * 2 - 1) / (NT * 2));
     want = std::max(want, 1);
     const char* eg = std::getenv("GLIMS_AMG_FUSED_GRID");
     if (eg) want = std::max(1, atoi(eg));
     // stay at one CTA per SM at most unless asked otherwise: the barrier cost grows with the CTA count
     f->grid = std::min(want, std::max(1, std::min(per_sm, 2) * sms));
-    delete P;
+    f->plan = P;
     return f;
 }
 
@@ -337,6 +448,23 @@ static void amg_fused_print_phases(Amg* amg) {
     fprintf(stderr, "glims amg fused kernel: grid %d, %d phases, %.1f us:", f->grid, f->n_phases, (t.back() - t[0]) * 1e-3);
     for (int i = 0; i < f->n_phases; ++i) fprintf(stderr, " %s@%d %.1f", names[f->ops[i]], f->lvls[i], (t[i + 1] - t[i]) * 1e-3);
     fprintf(stderr, "\n");
+    std::vector<unsigned long long> t2(4 * f->n_phases);
+    cudaMemcpy(t2.data(), f->tstamp + 128, sizeof(unsigned long long) * t2.size(), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "glims amg fused kernel, CTA 0 inside the matrix phases [start->dot, dot->sync, sync->end, end->barrier done]:");
+    for (int i = 0; i < f->n_phases; ++i)
+        if (f->ops[i] == FOP_STEP || f->ops[i] == FOP_RESID)
+            fprintf(stderr, " %s@%d [%.1f %.1f %.1f %.1f | phase start->dot start %.1f]", names[f->ops[i]], f->lvls[i], (t2[4 * i + 1] - t2[4 * i]) * 1e-3,
+                    (t2[4 * i + 2] - t2[4 * i + 1]) * 1e-3, (t2[4 * i + 3] - t2[4 * i + 2]) * 1e-3, (t[i + 1] - t2[4 * i + 3]) * 1e-3, (t2[4 * i] - t[i]) * 1e-3);
+    fprintf(stderr, "\n");
+    {
+        const int g = std::min(f->grid, 512);
+        std::vector<unsigned long long> tc(g), sm(g);
+        cudaMemcpy(tc.data(), f->tstamp + 1024, sizeof(unsigned long long) * g, cudaMemcpyDeviceToHost);
+        cudaMemcpy(sm.data(), f->tstamp + 1536, sizeof(unsigned long long) * g, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "glims amg fused kernel, phase 2: work-done time of every CTA after the phase start (us) [cta:sm]:");
+        for (int i = 0; i < g; ++i) fprintf(stderr, " %d:%llu=%.1f", i, sm[i], ((double)tc[i] - (double)t[2]) * 1e-3);
+        fprintf(stderr, "\n");
+    }
 }
 
 // true: levels li+1.. ran fused (r32 of level li restricted, result prolonged into cur)
@@ -346,9 +474,9 @@ static bool amg_fused_run(glims_ctx* c, Amg* amg, int li, float* cur) {
     if (!enabled) return false;
     FusedHost* f = (FusedHost*)amg->fused;
     if (!f) { f = amg_fused_build(c, amg, li, cur); amg->fused = f; }
-    if (!f->dev || f->top_cur != cur || f->top_level != li) return false;
-    if (amg->dim == 2) k_amg_fused<2><<<f->grid, 96, 0, c->stream>>>(f->dev);
-    else k_amg_fused<3><<<f->grid, 192, 0, c->stream>>>(f->dev);
+    if (!f->plan || f->top_cur != cur || f->top_level != li) return false;
+    if (amg->dim == 2) k_amg_fused<2><<<f->grid, 96 * FUSED_CG, 0, c->stream>>>(*f->plan);
+    else k_amg_fused<3><<<f->grid, 192 * FUSED_CG, 0, c->stream>>>(*f->plan);
     c->launches++;
     return true;
 }

@@ -613,4 +613,12 @@ void cc_compute_lift(glims_ctx* c, bool any_nonzero) {
     fu_launch(c, tmp, nullptr, nullptr, m->lift, c->dim);
 }
 
+// the P1 mass matrix in the SELL slots of the vertex pattern (null when the pair lists cannot represent the mesh)
+const double* cc_mass_matrix(glims_ctx* c) {
+    CcMap* m = cc_ensure(c);
+    if (!m->ok) return nullptr;
+    cc_ensure_consts(c, m);
+    return m->Mass;
+}
+
 i64 cc_map_bytes(glims_ctx* c) { CcMap* m = (CcMap*)c->ccmap; return m ? (i64)m->map_bytes : 0; }

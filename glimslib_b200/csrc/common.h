@@ -115,6 +115,7 @@ struct glims_ctx {
     double* dinv_uu = nullptr;  // [n_v][dim*dim] inverse diagonal blocks of K_uu
     double* dinv_cc = nullptr;  // [n_v]
     double* dinv_mono = nullptr;// [n_v][nb*nb]
+    double* dinv_mass = nullptr;// [n_v] inverse diagonal of the P1 mass matrix (L2 projections)
 
     // vectors, vertex-blocked [n_v][nb]
     double *x = nullptr, *xprev = nullptr, *F = nullptr, *fext = nullptr, *dx = nullptr;
@@ -172,6 +173,7 @@ bool launch_cc_rows(glims_ctx* c, bool with_kcc, bool with_res);   // K_cc and/o
 void launch_fu(glims_ctx* c, bool eliminated);       // F_u = K_uu u + K_uc c (+ lift) - f_ext from the stored blocks
 void cc_compute_lift(glims_ctx* c, bool any_nonzero);// while K_uu / K_uc are raw
 i64 cc_map_bytes(glims_ctx* c);
+const double* cc_mass_matrix(glims_ctx* c);          // P1 mass matrix over the vertex pattern (scalar SELL values)
 
 // ---------------- kernels.cu (launch wrappers; all on c->stream)
 void launch_assemble(glims_ctx* c, int what, int variant);
@@ -214,6 +216,9 @@ void launch_insert_add(glims_ctx* c, double* xb, const double* du, const double*
 void launch_split_norms(glims_ctx* c, const double* F, int s0);   // |F_u|^2, |F_c|^2 -> slots s0, s0+1
 void launch_multi_axpy(glims_ctx* c, const double* V, i64 ld, int k, const double* coef_dev, double sign, double* w, i64 n);
 void read_scalars(glims_ctx* c, int slot0, int n, double* out);   // sync
+void launch_project_load(glims_ctx* c, const double* q, const double* vol, double* load);   // load[n_v][nf] = int f phi
+void launch_strided_copy(glims_ctx* c, const double* src, i64 n, int ss, int os, double* dst, int sd, int od);
+void launch_scalar_diag_inverse(glims_ctx* c, const double* A, double* out);
 void flush_l2(glims_ctx* c);
 void launch_permute(glims_ctx* c, const double* src, double* dst, const i64* perm, i64 n, bool scatter);  // scatter: dst[perm[i]] = src[i]
 

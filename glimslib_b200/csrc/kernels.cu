@@ -450,6 +450,77 @@ __global__ void k_cell_fields(const double* __restrict__ coords, const int* __re
     vol_out[e] = G.vol;
 }
 
+// Right-hand side of the consistent-mass L2 projection onto P1 of the derived fields (the reference's `project(expr, V)`,
+// helper_classes.py:1560-1618): load[v][f] = int f(x) phi_v dx.  Fields that are constant per cell (strain, stress, pressure,
+// von Mises, det(I + grad u)) give |K|/(d+1) f; the two that are polynomials of the P1 concentration -- det(I + c gamma I) =
+// (1 + gamma c)^d and rho c (1 - c) -- are integrated exactly with int lambda^alpha = |K| d! alpha! / (|alpha| + d)!.
+__device__ inline double fact_prod4(int a, int b, int c, int e) {        // prod_i (multiplicity of i)!  over the given indices (-1: unused)
+    const int idx[4] = {a, b, c, e};
+    double f = 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (idx[i] < 0) continue;
+        int m = 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < i && idx[j] == idx[i]) ++m;       // this occurrence is the m-th of its value: contributes the factor m
+        f *= (double)m;
+    }
+    return f;
+}
+template <int D>
+__global__ void k_project_load(const int* __restrict__ cells, i64 n_c, const double* __restrict__ q, const double* __restrict__ vol,
+                               const int* __restrict__ cell_mat, const double* __restrict__ mat_g, const double* __restrict__ x,
+                               double* load) {
+    constexpr int NB = D + 1, NF = 2 * D * D + 5;
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= n_c) return;
+    int v[NB];
+    double cv[NB];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) { v[a] = cells[e * NB + a]; cv[a] = x[(i64)v[a] * NB + D]; }
+    const double w = vol[e], rho = mat_g[cell_mat[e] * MAT_STRIDE + 3], gam = mat_g[cell_mat[e] * MAT_STRIDE + 4];
+    // d! / (k + 1 + d)!  for k = 0..3 (k = polynomial degree in c, +1 for the test function)
+    double fac[4];
+    {
+        double dfact = (D == 2) ? 2.0 : 6.0, den = dfact;           // d!
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { den *= (double)(k + 1 + D); fac[k] = dfact / den; }
+    }
+#pragma unroll
+    for (int a = 0; a < NB; ++a) {
+        double I0 = w * fac[0], I1 = 0, I2 = 0, I3 = 0;               // int lambda_a c^k
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            I1 += cv[b] * fact_prod4(a, b, -1, -1);
+#pragma unroll
+            for (int c2 = 0; c2 < NB; ++c2) {
+                I2 += cv[b] * cv[c2] * fact_prod4(a, b, c2, -1);
+                if (D == 3) {
+#pragma unroll
+                    for (int e3 = 0; e3 < NB; ++e3) I3 += cv[b] * cv[c2] * cv[e3] * fact_prod4(a, b, c2, e3);
+                }
+            }
+        }
+        I1 *= w * fac[1]; I2 *= w * fac[2]; I3 *= w * fac[3];
+        double* o = load + (i64)v[a] * NF;
+        for (int f = 0; f < 2 * D * D + 3; ++f) atomicAdd(&o[f], I0 * q[e * NF + f]);
+        const double jg = (D == 2) ? I0 + 2.0 * gam * I1 + gam * gam * I2
+                                   : I0 + 3.0 * gam * I1 + 3.0 * gam * gam * I2 + gam * gam * gam * I3;
+        atomicAdd(&o[2 * D * D + 3], jg);
+        atomicAdd(&o[2 * D * D + 4], rho * (I1 - I2));
+    }
+}
+__global__ void k_strided_copy(const double* __restrict__ src, i64 n, int stride_src, int off_src, double* __restrict__ dst,
+                               int stride_dst, int off_dst) {
+    for (i64 i = blockIdx.x * (i64)TPB + threadIdx.x; i < n; i += (i64)gridDim.x * TPB)
+        dst[i * stride_dst + off_dst] = src[i * stride_src + off_src];
+}
+__global__ void k_scalar_diag_inverse(const int* __restrict__ diag, int n_rows, const double* __restrict__ A, double* out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows) out[r] = 1.0 / A[diag[r]];
+}
+
 // volume-weighted nodal average of per-cell fields: num[v][f] += vol*q, den[v] += vol
 __global__ void k_cell_to_vertex(const int* __restrict__ cells, int nb, i64 n_c, int nf, const double* __restrict__ q,
                                  const double* __restrict__ vol, double* num, double* den) {
@@ -1084,8 +1155,9 @@ void launch_spmv(glims_ctx* c, int which, const double* x, double* y, SpmvDot do
         else             { if (d) k_spmv_block<3, 3, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS);
                            else k_spmv_block<3, 3, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS); }
     } else {
-        if (d) k_spmv_block<1, 1, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kcc, x, y, ARGS);
-        else k_spmv_block<1, 1, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kcc, x, y, ARGS);
+        const double* A = which == 3 ? cc_mass_matrix(c) : c->Kcc;      // 3: the P1 mass matrix (L2 projections)
+        if (d) k_spmv_block<1, 1, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, ARGS);
+        else k_spmv_block<1, 1, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, ARGS);
     }
 #undef ARGS
     LAUNCHED(c);
@@ -1192,6 +1264,21 @@ void launch_cell_to_vertex(glims_ctx* c, int nf, const double* q, const double* 
     k_cell_to_vertex<<<nblk(c->n_c), TPB, 0, c->stream>>>(c->cells, c->nb, c->n_c, nf, q, vol, num, den);
     k_divide_rows<<<nblk(c->n_v * nf), TPB, 0, c->stream>>>(num, den, c->n_v, nf);
     c->launches += 2;
+}
+void launch_project_load(glims_ctx* c, const double* q, const double* vol, double* load) {
+    const int nf = 2 * c->dim * c->dim + 5;
+    GL_CUDA(cudaMemsetAsync(load, 0, sizeof(double) * c->n_v * nf, c->stream));
+    if (c->dim == 2) k_project_load<2><<<nblk(c->n_c, 128), 128, 0, c->stream>>>(c->cells, c->n_c, q, vol, c->cell_mat, c->mat, c->x, load);
+    else k_project_load<3><<<nblk(c->n_c, 128), 128, 0, c->stream>>>(c->cells, c->n_c, q, vol, c->cell_mat, c->mat, c->x, load);
+    LAUNCHED(c);
+}
+void launch_strided_copy(glims_ctx* c, const double* src, i64 n, int ss, int os, double* dst, int sd, int od) {
+    k_strided_copy<<<red_grid(c, n), TPB, 0, c->stream>>>(src, n, ss, os, dst, sd, od);
+    LAUNCHED(c);
+}
+void launch_scalar_diag_inverse(glims_ctx* c, const double* A, double* out) {
+    k_scalar_diag_inverse<<<nblk(c->pat.n_rows), TPB, 0, c->stream>>>(c->pat.diag, c->pat.n_rows, A, out);
+    LAUNCHED(c);
 }
 void launch_extrapolate_c(glims_ctx* c, double* x, const double* xold) {
     if (c->dim == 2) k_extrapolate_c<2><<<red_grid(c, c->n_v), TPB, 0, c->stream>>>(x, xold, c->n_v);

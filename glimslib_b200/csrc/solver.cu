@@ -7,6 +7,7 @@
 #include <map>
 #include <tuple>
 #include <cstdlib>
+#include <chrono>
 
 void launch_split_norms(glims_ctx* c, const double* F, int s0);
 void launch_pcg_shift(glims_ctx* c, double* ring);
@@ -90,6 +91,7 @@ i64 nrows(glims_ctx* c) { return c->pat.n_rows; }
 // preconditioner application z = M^-1 r, rz -> slot
 void apply_pc(glims_ctx* c, int which, int pc, const double* r, double* z, int s_rz) {
     if (which == 2) { launch_block_jacobi(c, c->dinv_cc, 1, r, z, nrows(c), s_rz); return; }
+    if (which == 3) { launch_block_jacobi(c, c->dinv_mass, 1, r, z, nrows(c), s_rz); return; }
     if (which == 1) {
         if ((pc == GLIMS_PC_AMG || pc == GLIMS_PC_AMG_FP64) && c->amg) {
             amg_vcycle(c, r, z, pc == GLIMS_PC_AMG);
@@ -170,7 +172,7 @@ int pcg(glims_ctx* c, int which, int pc, const double* b, double* x, double tol_
         int maxit, double* res_out, bool recycle = false) {
     const int bs = which == 1 ? c->dim : 1;
     const i64 n = nrows(c) * bs, nl = c->n_v * bs;
-    const char* tag = which == 1 ? "u" : "c";
+    const char* tag = which == 1 ? "u" : which == 3 ? "m" : "c";
     char nm[32];
     auto W = [&](const char* base) { snprintf(nm, sizeof nm, "cg_%s_%s", base, tag); return ws(c, nm, nl); };
     double *r = W("r"), *p = W("p"), *Ap = W("Ap"), *z = W("z");
@@ -758,7 +760,7 @@ int glims_destroy(glims_ctx* c) {
                     (void*)c->gent, (void*)c->Kuu, (void*)c->Kuc, (void*)c->Kcc, (void*)c->dinv_uu, (void*)c->dinv_cc,
                     (void*)c->dinv_mono, (void*)c->x, (void*)c->xprev, (void*)c->F, (void*)c->fext, (void*)c->dx,
                     (void*)c->bc_dofs, (void*)c->bc_vals, (void*)c->bcmask, (void*)c->scal, (void*)c->partials,
-                    (void*)c->tickets, (void*)c->flush_buf, (void*)c->sl_ptr, (void*)c->sl_elem, (void*)c->lent, (void*)c->halo.send_idx, (void*)c->halo.send_buf, (void*)c->dof_perm})
+                    (void*)c->tickets, (void*)c->flush_buf, (void*)c->sl_ptr, (void*)c->sl_elem, (void*)c->lent, (void*)c->halo.send_idx, (void*)c->halo.send_buf, (void*)c->dof_perm, (void*)c->dinv_mass})
         if (q) cudaFree(q);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_ring) cudaFreeHost(c->h_ring);
@@ -926,9 +928,19 @@ int glims_prepare(glims_ctx* c, const glims_solver_opts* o) {
     if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_prepare before glims_set_materials");
     glims_solver_opts od;
     if (!o) { glims_default_opts(&od); o = &od; }
-    ensure_kconst(c, o);
-    if (use_rows(c, o)) cc_mass_cprev(c);        // also builds the per-slot constants
+    const bool verbose = std::getenv("GLIMS_VERBOSE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    const bool rows = use_rows(c, o);            // builds the (row, element) pair lists on first use
     GL_CUDA(cudaStreamSynchronize(c->stream));
+    double t1 = now();
+    ensure_kconst(c, o);
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    double t2 = now();
+    if (rows) cc_mass_cprev(c);                  // also builds the per-slot constants
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    double t3 = now();
+    if (verbose) fprintf(stderr, "glims prepare: pair lists %.3f s, K_uu/K_uc + elimination + AMG %.3f s, per-slot constants %.3f s\n", t1 - t0, t2 - t1, t3 - t2);
     API_END
 }
 
@@ -1042,6 +1054,58 @@ int glims_cell_fields(glims_ctx* c, double* cell_out, double* vertex_out) {
         launch_cell_to_vertex(c, nf, q, vol, num, den);
         GL_CUDA(cudaMemcpyAsync(vertex_out, num, sizeof(double) * c->n_v * nf, cudaMemcpyDeviceToHost, c->stream));
     }
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_project_fields(glims_ctx* c, double* vertex_out) {
+    API_BEGIN
+    if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_project_fields before glims_set_materials");
+    if (!vertex_out) throw GlError(GLIMS_ERR_ARG, "glims_project_fields: null output");
+    const double* M = cc_mass_matrix(c);
+    if (!M) throw GlError(GLIMS_ERR_STATE, std::string("glims_project_fields: mass matrix unavailable: ") + cc_status(c));
+    const int nf = 2 * c->dim * c->dim + 5;
+    const i64 nr = nrows(c);
+    double *q = ws(c, "pp_q", c->n_c * nf), *vol = ws(c, "pp_vol", c->n_c), *load = ws(c, "pp_load", c->n_v * nf);
+    double *out = ws(c, "pp_proj", c->n_v * nf), *b = ws(c, "pp_b", c->n_v), *xq = ws(c, "pp_x", c->n_v);
+    halo_exchange(c, c->x, c->nb);
+    launch_cell_fields(c, q, vol);
+    launch_project_load(c, q, vol, load);
+    if (!c->dinv_mass) GL_CUDA(cudaMalloc(&c->dinv_mass, sizeof(double) * nr));
+    launch_scalar_diag_inverse(c, M, c->dinv_mass);
+    launch_zero(c, out, c->n_v * nf);
+    for (int f = 0; f < nf; ++f) {
+        launch_strided_copy(c, load, nr, nf, f, b, 1, 0);
+        double res = 0;
+        int its = pcg(c, 3, GLIMS_PC_JACOBI, b, xq, 1e-13, 0.0, 1e-300, 2000, &res);
+        if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "glims_project_fields: mass-matrix CG did not converge");
+        launch_strided_copy(c, xq, nr, 1, 0, out, nf, f);
+    }
+    GL_CUDA(cudaMemcpyAsync(vertex_out, out, sizeof(double) * c->n_v * nf, cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int glims_mass_solve(glims_ctx* c, int32_t nf, const double* load, double* out) {
+    API_BEGIN
+    if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_mass_solve before glims_set_materials");
+    if (nf <= 0 || !load || !out) throw GlError(GLIMS_ERR_ARG, "glims_mass_solve: bad arguments");
+    const double* M = cc_mass_matrix(c);
+    if (!M) throw GlError(GLIMS_ERR_STATE, std::string("glims_mass_solve: mass matrix unavailable: ") + cc_status(c));
+    const i64 nr = nrows(c);
+    double *dl = ws(c, "ms_load", c->n_v * nf), *dout = ws(c, "ms_out", c->n_v * nf), *b = ws(c, "pp_b", c->n_v), *xq = ws(c, "pp_x", c->n_v);
+    GL_CUDA(cudaMemcpyAsync(dl, load, sizeof(double) * c->n_v * nf, cudaMemcpyHostToDevice, c->stream));
+    if (!c->dinv_mass) GL_CUDA(cudaMalloc(&c->dinv_mass, sizeof(double) * nr));
+    launch_scalar_diag_inverse(c, M, c->dinv_mass);
+    launch_zero(c, dout, c->n_v * nf);
+    for (int f = 0; f < nf; ++f) {
+        launch_strided_copy(c, dl, nr, nf, f, b, 1, 0);
+        double res = 0;
+        int its = pcg(c, 3, GLIMS_PC_JACOBI, b, xq, 1e-13, 0.0, 1e-300, 2000, &res);
+        if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "glims_mass_solve: mass-matrix CG did not converge");
+        launch_strided_copy(c, xq, nr, 1, 0, dout, nf, f);
+    }
+    GL_CUDA(cudaMemcpyAsync(out, dout, sizeof(double) * c->n_v * nf, cudaMemcpyDeviceToHost, c->stream));
     GL_CUDA(cudaStreamSynchronize(c->stream));
     API_END
 }

@@ -233,6 +233,33 @@ class Engine:
             res[name] = out[:, 2 * d * d + k]
         return res
 
+    def project_fields(self):
+        """The derived fields of :meth:`cell_fields` L2-projected onto P1 with the consistent mass matrix (what the
+        reference's ``fenics.project`` returns), all on the device.  Dict of per-vertex arrays in the caller's order."""
+        d = self.dim
+        nf = 2 * d * d + 5
+        n = self.n_vertices
+        out = np.empty((n, nf))
+        self._check(self._lib.glims_project_fields(self._h, N.as_dp(out)), "project_fields")
+        if self._new_of_old is not None:
+            out = out[self._new_of_old]
+        res = {"strain": out[:, :d * d].reshape(n, d, d), "stress": out[:, d * d:2 * d * d].reshape(n, d, d)}
+        for k, name in enumerate(self.FIELD_NAMES[2:]):
+            res[name] = out[:, 2 * d * d + k]
+        return res
+
+    def mass_solve(self, load):
+        """``M^-1 load`` column by column (``load``: [n_vertices, nf] in the caller's vertex order), M = P1 mass matrix."""
+        a = N.f64(load)
+        a = a.reshape(self.n_vertices, -1)
+        if self._new_of_old is not None:
+            old_of_new = np.empty_like(self._new_of_old)
+            old_of_new[self._new_of_old] = np.arange(self.n_vertices)
+            a = np.ascontiguousarray(a[old_of_new])
+        out = np.empty_like(a)
+        self._check(self._lib.glims_mass_solve(self._h, a.shape[1], N.as_dp(a), N.as_dp(out)), "mass_solve")
+        return out[self._new_of_old] if self._new_of_old is not None else out
+
     def time_kernel(self, kernel, variant=0, reps=10, flush_l2=True):
         ms = C.c_float()
         self._check(self._lib.glims_time_kernel(self._h, kernel, variant, reps, int(flush_l2), C.byref(ms)), "time_kernel")

@@ -185,6 +185,15 @@ int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t rep
    rho*cbar*(1-cbar)].  cell_out[n_cells][nf] and/or vertex_out[n_vertices][nf] (volume-weighted nodal average);
    either may be NULL. */
 int glims_cell_fields(glims_ctx* c, double* cell_out, double* vertex_out);
+/* The same fields L2-projected onto P1 with the CONSISTENT mass matrix -- what the reference's `project(expr, V)` returns
+   (helper_classes.py:1560-1618, fenics_local project: M q = int f phi, here by Jacobi-PCG on the device to 1e-13).  Fields
+   constant per cell are integrated against the hat functions exactly; det(I + c gamma I) and rho c (1 - c) are polynomials
+   of the P1 concentration and are integrated exactly as well.  vertex_out[n_vertices][nf], vertex order of glims_create. */
+int glims_project_fields(glims_ctx* c, double* vertex_out);
+/* Generic consistent-mass L2 solve: out[:, f] = M^-1 load[:, f] for nf right-hand sides load[n_vertices][nf] (host), M the P1
+   mass matrix of the mesh -- the linear solve inside every `fenics.project(expr, V)` of the reference's post-processing
+   (helper_classes.py:1566-1618); the caller integrates `expr` against the hat functions. */
+int glims_mass_solve(glims_ctx* c, int32_t nf, const double* load, double* out);
 /* Tile-assembly map statistics (after the first GLIMS_ASMK_TILE assembly): info[0..7] = max local vertices, max element
    records, max contributor entries, max items, max partial buffers per slice, shared-memory bytes per CTA, device bytes of
    the maps, threads per CTA.  Returns GLIMS_ERR_STATE when the maps were not built or cannot represent the mesh. */
