@@ -552,10 +552,12 @@ static void cc_rows_dim(glims_ctx* c, CcMap* m, bool with_kcc, bool with_res) {
     const int g = nblk(p.n_slices, CC_TPB / 32);
     const double* fext = c->have_load ? c->fext : nullptr;
     const int mw = std::max(p.max_w, 1), mpw = std::max(m->max_pw, 4);
-    // bulk-copy variant when the per-warp stage (strips + whole list of the slice) leaves at least two CTAs per SM
+    // Bulk-copy variant (GLIMS_CC_TMA=1): measured SLOWER than the register-prefetch kernel at C4 (0.58 vs 0.33 ms): its
+    // 74 KB per CTA leave 12 warps per SM, too few to cover the latency of the column / Klin / K_cc accesses that still go
+    // through ordinary loads (profiles/r02_ncu_summary.md).  Kept selectable; the default is the register-prefetch kernel.
     const size_t smem_tma = (size_t)(CC_TPB / 32) * (2 * (size_t)mw * 256 + (size_t)mpw * 384);
-    static const bool no_tma = std::getenv("GLIMS_CC_NO_TMA") != nullptr;
-    if (!no_tma && smem_tma <= 100 * 1024) {
+    static const bool use_tma = [] { const char* e = std::getenv("GLIMS_CC_TMA"); return e && atoi(e) != 0; }();
+    if (use_tma && smem_tma <= 100 * 1024) {
 #define CC_TMA(WK) do { auto kfn = k_cc_rows_tma<D, WK>; \
         GL_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma)); \
         kfn<<<g, CC_TPB, smem_tma, c->stream>>>(p.slice_off, p.slice_w, p.col, p.n_rows, p.n_slices, m->pl_off, m->pl_w, m->prv, \

@@ -84,3 +84,4 @@ class TumorGrowth(FenicsSimulation):
     def init_postprocess(self, output_dir=config.output_dir_simulation_tmp):
         self.postprocess = PostProcessTumorGrowth(self.results, self.params, output_dir=output_dir,
                                                   engine=getattr(getattr(self, "solver", None), "_engine", None))
+        self.postprocess._form = getattr(getattr(getattr(self, "solver", None), "problem", None), "form", None)

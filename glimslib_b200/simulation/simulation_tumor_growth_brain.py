@@ -65,3 +65,4 @@ class TumorGrowthBrain(TumorGrowth):
     def init_postprocess(self, output_dir=config.output_dir_simulation_tmp):
         self.postprocess = PostProcessTumorGrowthBrain(self.results, self.params, output_dir=output_dir,
                                                        engine=getattr(getattr(self, "solver", None), "_engine", None))
+        self.postprocess._form = getattr(getattr(getattr(self, "solver", None), "problem", None), "form", None)

@@ -762,11 +762,19 @@ class Plotting:
 class PostProcessTumorGrowth:
     """Derived fields of recorded solutions (reference: helper_classes.py:1560-1618,1736-1786).
 
-    The reference L2-projects UFL expressions (one CG+AMG solve per field per step).  With P1 displacement, strain,
-    stress, pressure, von Mises and det(I + grad u) are constant per cell, so here one device kernel evaluates them per
-    cell (``glims_cell_fields``) and, for the P1 fields the reference returns, takes the volume-weighted nodal average
-    (the lumped-mass L2 projection).  ``cellwise=True`` returns the exact per-cell (DG0) values instead.
-    Plotting / ALE mesh motion stay out of scope."""
+    The reference L2-projects UFL expressions onto P1 (``fenics.project``: one CG+AMG solve per field per step).  Here
+
+    * strain, stress, det(I + grad u), the logistic term and the growth expansion are integrated against the hat functions
+      exactly on the device (constant per cell, or polynomial in the P1 concentration) and the consistent-mass systems are
+      solved there by Jacobi-PCG (``glims_project_fields`` / ``glims_mass_solve``): the reference's projections;
+    * pressure is ``tr(stress_h)/3`` of the projected stress -- the reference projects that P1 function once more, which
+      returns it unchanged (helper_classes.py:1586-1592);
+    * von Mises stress, the growth-induced Jacobian and the displacement norm are built, as in the reference, from the
+      already projected functions and projected again; their load vectors are integrated on the host with a degree-5 rule
+      (``backend/projection.py``), the mass solves run on the device.
+
+    ``cellwise=True`` returns the exact per-cell (DG0) values instead, ``lumped=True`` the volume-weighted nodal averages
+    (lumped-mass projection, one kernel, no solve).  Plotting / ALE mesh motion stay out of scope."""
 
     def __init__(self, results, params, output_dir=None, plot_params=None, engine=None):
         self.logger = logging.getLogger(__name__)
@@ -784,12 +792,23 @@ class PostProcessTumorGrowth:
     def get_solution_concentration(self, recording_step=None):
         return self._results.get_solution_function(subspace_name="concentration", recording_step=recording_step)
 
-    def _fields(self, recording_step, cellwise):
+    def _need_engine(self):
         if self._engine is None:
             raise RuntimeError("post-processing needs the simulation's engine: call sim.init_postprocess() after sim.run()")
+        return self._engine
+
+    def _fields(self, recording_step, cellwise, lumped=False):
+        eng = self._need_engine()
         u = self._results.get_solution_function(recording_step=recording_step)
-        self._engine.set_state(u.vector().get_local())
-        return self._engine.cell_fields(vertex=not cellwise)
+        eng.set_state(u.vector().get_local())
+        if cellwise:
+            return eng.cell_fields(vertex=False)
+        return eng.cell_fields(vertex=True) if lumped else eng.project_fields()
+
+    def _project(self, integrand, n_comp=1):
+        """fenics.project of an expression given at quadrature points: host load vector + device consistent-mass solve."""
+        from glimslib_b200.backend import projection
+        return self._need_engine().mass_solve(projection.load_vector(self._mesh, integrand, n_comp))
 
     def _as_function(self, values, name, cellwise, tensor=False):
         fam, deg = ("DG", 0) if cellwise else ("Lagrange", 1)
@@ -798,30 +817,69 @@ class PostProcessTumorGrowth:
         f.vector().set_local(np.asarray(values).reshape(-1))
         return f
 
-    def get_strain_tensor(self, recording_step=None, cellwise=False):
-        return self._as_function(self._fields(recording_step, cellwise)["strain"], "strain_tensor", cellwise, tensor=True)
+    def get_strain_tensor(self, recording_step=None, cellwise=False, lumped=False):
+        return self._as_function(self._fields(recording_step, cellwise, lumped)["strain"], "strain_tensor", cellwise, tensor=True)
 
-    def get_stress_tensor(self, recording_step=None, cellwise=False):
-        return self._as_function(self._fields(recording_step, cellwise)["stress"], "stress_tensor", cellwise, tensor=True)
+    def get_stress_tensor(self, recording_step=None, cellwise=False, lumped=False):
+        return self._as_function(self._fields(recording_step, cellwise, lumped)["stress"], "stress_tensor", cellwise, tensor=True)
 
-    def get_pressure(self, recording_step=None, cellwise=False):
-        return self._as_function(self._fields(recording_step, cellwise)["pressure"], "pressure", cellwise)
+    def get_pressure(self, recording_step=None, cellwise=False, lumped=False):
+        f = self._fields(recording_step, cellwise, lumped)
+        if cellwise or lumped:
+            return self._as_function(f["pressure"], "pressure", cellwise)
+        return self._as_function(np.trace(f["stress"], axis1=1, axis2=2) / 3.0, "pressure", False)
 
-    def get_van_mises_stress(self, recording_step=None, cellwise=False):
-        return self._as_function(self._fields(recording_step, cellwise)["von_mises"], "van_mises_stress", cellwise)
+    def get_van_mises_stress(self, recording_step=None, cellwise=False, lumped=False):
+        f = self._fields(recording_step, cellwise, lumped)
+        if cellwise or lumped:
+            return self._as_function(f["von_mises"], "van_mises_stress", cellwise)
+        sh, d = f["stress"], self._mesh.dim
+        eye = np.eye(d)
 
-    def get_total_jacobian(self, recording_step=None, cellwise=False):
-        return self._as_function(self._fields(recording_step, cellwise)["total_jacobian"], "total_jacobian", cellwise)
+        def vm(cells, lam, sl):
+            s = np.einsum("qa,eaij->eqij", lam, sh[cells])
+            dev = s - (np.trace(s, axis1=2, axis2=3) / 3.0)[:, :, None, None] * eye
+            return np.sqrt(1.5 * np.einsum("eqij,eqij->eq", dev, dev))
+        return self._as_function(self._project(vm)[:, 0], "van_mises_stress", False)
 
-    def get_growth_induced_jacobian(self, recording_step=None, cellwise=False):
-        return self._as_function(self._fields(recording_step, cellwise)["growth_jacobian"], "growth_induced_jacobian", cellwise)
+    def get_total_jacobian(self, recording_step=None, cellwise=False, lumped=False):
+        return self._as_function(self._fields(recording_step, cellwise, lumped)["total_jacobian"], "total_jacobian", cellwise)
 
-    def get_logistic_growth(self, recording_step=None, cellwise=False):
-        return self._as_function(self._fields(recording_step, cellwise)["logistic_growth"], "log_growth", cellwise)
+    def _cell_coupling(self):
+        form = self._engine_form()
+        return form.table[form.cell_mat, 4]
 
-    def get_displacement_norm(self, recording_step=None):
-        u = self.get_solution_displacement(recording_step=recording_step)
-        return self._as_function(np.linalg.norm(u.node_values(), axis=1), "displacement_norm", False)
+    def _engine_form(self):
+        form = getattr(self, "_form", None)
+        if form is None:
+            raise RuntimeError("post-processing needs the problem description: call sim.init_postprocess() after sim.run()")
+        return form
+
+    def get_mech_expansion(self, recording_step=None):
+        """project(c * coupling * I): returned as its scalar factor times the identity (helper_classes.py:1755-1762)."""
+        c = self.get_solution_concentration(recording_step=recording_step).vector().get_local()
+        gam = self._cell_coupling()
+        s = self._project(lambda cells, lam, sl: np.einsum("qa,ea->eq", lam, c[cells]) * gam[sl][:, None])[:, 0]
+        d = self._mesh.dim
+        return self._as_function(s[:, None, None] * np.eye(d)[None], "mech_expansion", False, tensor=True)
+
+    def get_growth_induced_jacobian(self, recording_step=None, cellwise=False, lumped=False):
+        if cellwise or lumped:
+            return self._as_function(self._fields(recording_step, cellwise, lumped)["growth_jacobian"], "growth_induced_jacobian", cellwise)
+        d = self._mesh.dim
+        s = self.get_mech_expansion(recording_step).vector().get_local().reshape(-1, d, d)[:, 0, 0]
+        jac = self._project(lambda cells, lam, sl: (1.0 + np.einsum("qa,ea->eq", lam, s[cells])) ** d)[:, 0]
+        return self._as_function(jac, "growth_induced_jacobian", False)
+
+    def get_logistic_growth(self, recording_step=None, cellwise=False, lumped=False):
+        return self._as_function(self._fields(recording_step, cellwise, lumped)["logistic_growth"], "log_growth", cellwise)
+
+    def get_displacement_norm(self, recording_step=None, lumped=False):
+        u = self.get_solution_displacement(recording_step=recording_step).node_values()
+        if lumped:
+            return self._as_function(np.linalg.norm(u, axis=1), "displacement_norm", False)
+        nrm = self._project(lambda cells, lam, sl: np.sqrt((np.einsum("qa,eai->eqi", lam, u[cells]) ** 2).sum(axis=2)))[:, 0]
+        return self._as_function(nrm, "displacement_norm", False)
 
     def plot_all(self, *a, **k):
         self.logger.warning("plotting is not part of the B200 hot path -- skipping plots")

@@ -140,5 +140,73 @@ def test_postprocess_fields_match_numpy(tmp_path):
     p_cell = np.trace(sig, axis1=1, axis2=2) / 3.0
     lumped = np.bincount(mesh.cells.ravel(), weights=np.repeat(V, 3), minlength=mesh.num_vertices())
     p_node = np.bincount(mesh.cells.ravel(), weights=np.repeat(V * p_cell, 3), minlength=mesh.num_vertices()) / lumped
-    assert np.abs(pp.get_pressure(10).vector().get_local() - p_node).max() <= 1e-12 * np.abs(p_node).max()
+    assert np.abs(pp.get_pressure(10, lumped=True).vector().get_local() - p_node).max() <= 1e-12 * np.abs(p_node).max()
     assert pp.get_displacement_norm(10).vector().get_local().max() > 0
+    # default getters = the reference's consistent-mass projections (oracle/postprocess.py), through the drop-in classes
+    from oracle import postprocess as opp
+    ref = opp.derived_fields(mesh.coords, mesh.cells, form.cell_mat, form.table, x.ravel())
+    rel = lambda a, b: np.abs(np.asarray(a).ravel() - np.asarray(b).ravel()).max() / np.abs(b).max()
+    assert rel(pp.get_stress_tensor(10).vector().get_local(), ref["stress"]) < 1e-9
+    assert rel(pp.get_pressure(10).vector().get_local(), ref["pressure"]) < 1e-9
+    assert rel(pp.get_van_mises_stress(10).vector().get_local(), ref["von_mises"]) < 1e-8
+    assert rel(pp.get_total_jacobian(10).vector().get_local(), ref["total_jacobian"]) < 1e-9
+    assert rel(pp.get_growth_induced_jacobian(10).vector().get_local(), ref["growth_jacobian"]) < 1e-8
+    assert rel(pp.get_logistic_growth(10).vector().get_local(), ref["logistic_growth"]) < 1e-9
+    assert rel(pp.get_displacement_norm(10).vector().get_local(), ref["displacement_norm"]) < 1e-8
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_projected_derived_fields_match_the_reference_projections(d):
+    """the post-processing fields as the reference computes them -- fenics.project(expr, V), i.e. the
+    consistent-mass L2 projection onto P1 (helper_classes.py:1566-1618, 1736-1786) -- against oracle/postprocess.py, which
+    integrates the UFL text of math_linear_elasticity.py:12-46 literally with a degree-5 rule and solves M q = b by sparse LU:
+    device-only fields (glims_project_fields) <= 1e-9, the staged ones (pressure / von Mises from the projected stress,
+    growth Jacobian from the projected expansion, displacement norm; host load + glims_mass_solve) <= 1e-8."""
+    from oracle import postprocess as opp, meshes
+    from glimslib_b200.engine import Engine
+    from glimslib_b200.backend import projection
+    from glimslib_b200 import mesh as gmesh
+    rng = np.random.default_rng(41)
+    if d == 2:
+        coords, cells = meshes.rectangle_mesh((0, 0), (1.0, 1.3), 9, 8)
+    else:
+        coords, cells = meshes.box_mesh((0, 0, 0), (1, 1.2, 0.8), 5, 4, 5)
+    bv = meshes.boundary_vertices(cells, len(coords))
+    interior = np.ones(len(coords), bool)
+    interior[bv] = False
+    coords = coords.copy()
+    coords[interior] += 0.03 * (rng.random((interior.sum(), d)) - 0.5)
+    cell_mat = rng.integers(0, 3, len(cells)).astype(np.int32)
+    mats = fem.Materials.from_E_nu([3e-3, 1e-3, 2e-3], [0.45, 0.3, 0.49], [0.1, 0.02, 0.0], [0.2, 0.05, 0.0], [0.15, 0.0, 0.3])
+    table = mats.table()
+    nb = d + 1
+    x = np.zeros((len(coords), nb))
+    x[:, :d] = 0.05 * rng.standard_normal((len(coords), d))
+    x[:, d] = rng.random(len(coords))
+    ref = opp.derived_fields(coords, cells, cell_mat, table, x.ravel())
+    eng = Engine(coords, cells, cell_mat)
+    eng.set_materials(table)
+    eng.set_state(x.ravel())
+    f = eng.project_fields()
+    rel = lambda a, b: np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+    assert rel(f["strain"], ref["strain"]) < 1e-9
+    assert rel(f["stress"], ref["stress"]) < 1e-9
+    assert rel(f["total_jacobian"], ref["total_jacobian"]) < 1e-9
+    assert rel(f["logistic_growth"], ref["logistic_growth"]) < 1e-9
+    assert rel(np.trace(f["stress"], axis1=1, axis2=2) / 3.0, ref["pressure"]) < 1e-9
+    # generic mass solve + host load: von Mises of the projected stress
+    mesh = gmesh.SimplexMesh(coords, cells)
+    sh, eye = f["stress"], np.eye(d)
+
+    def vm(cc, lam, sl):
+        s = np.einsum("qa,eaij->eqij", lam, sh[cc])
+        dev = s - (np.trace(s, axis1=2, axis2=3) / 3.0)[:, :, None, None] * eye
+        return np.sqrt(1.5 * np.einsum("eqij,eqij->eq", dev, dev))
+    got = eng.mass_solve(projection.load_vector(mesh, vm))[:, 0]
+    assert rel(got, ref["von_mises"]) < 1e-8
+    gam = table[cell_mat, 4]
+    mech = eng.mass_solve(projection.load_vector(mesh, lambda cc, lam, sl: np.einsum("qa,ea->eq", lam, x[:, d][cc]) * gam[sl][:, None]))[:, 0]
+    assert rel(mech, ref["mech_expansion"]) < 1e-8
+    jac = eng.mass_solve(projection.load_vector(mesh, lambda cc, lam, sl: (1.0 + np.einsum("qa,ea->eq", lam, mech[cc])) ** d))[:, 0]
+    assert rel(jac, ref["growth_jacobian"]) < 1e-8
+    eng.close()
