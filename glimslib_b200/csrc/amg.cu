@@ -877,6 +877,7 @@ void vcycle32(glims_ctx* c, Amg* amg, int li, float* b, float* x) {
     const int n_own = dr ? l.rows : l.n;
     const i64 seg = (i64)n_own * l.bs;
     auto gather = [&](float* v) { if (dr) allgather_f32(c, l.sym, v, seg); };
+    if (li == 1 && amg_fused_run_full(c, amg, li, b, x)) return;
     if (li == (int)amg->L.size() - 1) {
         int m = amg->coarse_m;
         gather(b);
@@ -932,7 +933,11 @@ void build_fp32(glims_ctx* c, Amg* amg) {
     for (auto& l : amg->L) {
         i64 na = l.pat.n_slots * l.bs * l.bs, nd = (i64)l.n * l.bs * l.bs, nv = std::max<i64>(l.n_cols, l.n) * l.bs;
         // default: the fine level only (the coarse-level kernels are latency bound: measured no gain); GLIMS_AMG_FP16=2: every smoothed level
-        const bool fine16 = want16 && &l != &amg->L.back() && na > 0 && (&l == &amg->L[0] || (e16 && atoi(e16) >= 2));
+        // GLIMS_AMG_FP16: 0 none, 1 (default) level 0, 3 levels 0 and 1 (level 1 streams 230 MB per pass at C4 on one GPU;
+        // the levels below it run in the fused kernel from FP32 copies), 2 every smoothed level (unfused coarse path)
+        const int m16 = e16 ? atoi(e16) : 1;
+        const bool fine16 = want16 && &l != &amg->L.back() && na > 0 &&
+                            (&l == &amg->L[0] || m16 == 2 || (m16 == 3 && amg->L.size() > 1 && &l == &amg->L[1]));
         if (fine16) {
             thrust::device_ptr<const double> ap(l.A);
             const double amax = thrust::transform_reduce(thrust::cuda::par.on(c->stream), ap, ap + na, AbsD(), 0.0, thrust::maximum<double>());

@@ -161,11 +161,9 @@ k_allreduce(const P2PDev* __restrict__ P, double* __restrict__ scal, int slot0, 
 
 // ---- symmetric buffers: one allocation per rank that every rank maps (AMG level-1 vectors, amg.cu) ----------------------
 // layout: [0,64) u64 flag[rank] | [64,72) u64 seq | [72,76) u32 pushed | [76,80) i32 error | [80,84) u32 left | data from 256
-constexpr size_t SYM_DATA = 256;
-struct SymDev {
-    int n_ranks, rank;
-    unsigned char* base[P2P_MAX_RANKS];
-};
+constexpr size_t SYM_DATA = SYM_DATA_OFFSET;
+typedef SymView SymDev;
+static_assert(P2P_MAX_RANKS == 8, "SymView holds eight ranks");
 
 // In-place allgather of [n_ranks][seg] floats at byte offset `off` of the symmetric buffer: every rank pushes its own
 // segment into the same place of every peer's buffer, publishes a sequence number and waits for the peers' numbers.
@@ -457,6 +455,9 @@ void sym_free(void* p) {
     if (sb->mine) cudaFree(sb->mine);
     delete sb;
 }
+
+bool sym_is_p2p(void* p) { SymBuf* sb = (SymBuf*)p; return sb && sb->p2p; }
+const SymView* sym_view(void* p) { return p ? &((SymBuf*)p)->host : nullptr; }
 
 void* sym_data(void* p) { return p ? ((SymBuf*)p)->mine + SYM_DATA : nullptr; }
 

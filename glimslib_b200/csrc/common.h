@@ -237,12 +237,18 @@ void allreduce_scalars(glims_ctx* c, int slot0, int n);      // in-place sum ove
 void comm_free(glims_ctx* c);                                // peer windows (NCCL communicator is left to process exit)
 void comm_check(glims_ctx* c);                               // throws if a peer-memory wait timed out
 void solver_free_graphs(glims_ctx* c);                       // solver.cu: drop captured PCG graphs (transport changed)
+// device-visible description of a symmetric buffer: base address of every rank's copy (own one included), indexed by rank.
+// Layout of a copy: [0,64) u64 flag[rank] | [64,72) u64 seq | [72,76) u32 pushed | [76,80) i32 error | [80,84) u32 left | data from 256
+struct SymView { int n_ranks, rank; unsigned char* base[8]; };
+constexpr size_t SYM_DATA_OFFSET = 256;
 // symmetric buffers: one allocation per rank mapped by every rank (collective alloc); allgather_f32 gathers, in place, a
 // float vector [n_ranks][seg] living inside such a buffer (peer-memory pushes, or ncclAllGather when peer memory is off)
 void* sym_alloc(glims_ctx* c, size_t bytes);
 void sym_free(void* sb);
 void* sym_data(void* sb);
 bool sym_check(void* sb);
+bool sym_is_p2p(void* sb);                    // every rank maps every other rank's copy (peer-memory path in use)
+const SymView* sym_view(void* sb);          // host copy of the view (valid while the buffer lives)
 void allgather_f32(glims_ctx* c, void* sb, float* buf, i64 seg);
 // setup-time collectives (synchronous)
 void comm_allreduce_max_i64(glims_ctx* c, long long* v, int n);
