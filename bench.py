@@ -470,9 +470,10 @@ def main():
             roof = {"bound": "hbm", "kernel": "k_spmv32_row_cheb<3,__half> (fused Chebyshev smoother step, fine level of the V-cycle)",
                     "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": k["frac"],
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this kernel on this
-                    # workload (profiles/r01_ncu_summary.md); only valid for the default mesh on one GPU
-                    "traffic": 788.5e6 if default_c4 else None,
-                    "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full)", "peak_source": peak_src}
+                    # workload (profiles/r02_ncu_summary.md); only valid for the default mesh on one GPU
+                    "traffic": 786.4e6 if default_c4 else None,
+                    "traffic_source": "profiles/r02_ncu_summary.md (ncu --set full, dram read 756.2 MB + write 30.2 MB)",
+                    "peak_source": peak_src}
         else:
             k = kernels["spmv_kuu"]
             roof = {"bound": "hbm", "kernel": "k_spmv_block<3,3> (K_uu SELL-32 SpMV inside PCG)", "achieved": k["achieved_gbs"],

@@ -541,18 +541,26 @@ template <int BS, typename MT>
 __device__ inline float split_row_dot(const i64 base, const int w, const int* __restrict__ col, const MT* __restrict__ A,
                                       const float* __restrict__ x, const int i, const int lane) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    // whole rounds of four: columns past the slice width are clamped to the last one and weighted by zero (no serial tail)
-    for (int j = 0; j < w; j += 4) {
+    // (a predicated whole-round form -- clamp the column, weight by zero -- was tried: on level 1, which streams 230 MB per
+    // pass, the clamped columns are real loads and the kernel got 10 % slower, 70 -> 77 us; the fused kernel of the
+    // latency-bound levels below uses that form, amg_fused.cuh)
+    int j = 0;
+    for (; j + 3 < w; j += 4) {
         int cc[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) cc[u] = __ldg(&col[base + (i64)min(j + u, w - 1) * 32 + lane]);
+        for (int u = 0; u < 4; ++u) cc[u] = __ldg(&col[base + (i64)(j + u) * 32 + lane]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const MT* Au = A + (base + (i64)min(j + u, w - 1) * 32) * (BS * BS) + (i * BS) * 32 + lane;
-            const float on = (j + u < w) ? 1.f : 0.f;
+            const MT* Au = A + (base + (i64)(j + u) * 32) * (BS * BS) + (i * BS) * 32 + lane;
 #pragma unroll
-            for (int b = 0; b < BS; ++b) acc[u] += on * ld_mat(&Au[b * 32]) * __ldg(&x[(i64)cc[u] * BS + b]);
+            for (int b = 0; b < BS; ++b) acc[u] += ld_mat(&Au[b * 32]) * __ldg(&x[(i64)cc[u] * BS + b]);
         }
+    }
+    for (; j < w; ++j) {
+        const int c0 = __ldg(&col[base + (i64)j * 32 + lane]);
+        const MT* A0 = A + (base + (i64)j * 32) * (BS * BS) + (i * BS) * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < BS; ++b) acc[0] += ld_mat(&A0[b * 32]) * __ldg(&x[(i64)c0 * BS + b]);
     }
     return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
