@@ -19,7 +19,7 @@ SYMBOLS = [
     "glims_stream", "glims_step", "glims_assemble", "glims_get_residual", "glims_export_pattern",
     "glims_export_values", "glims_spmv", "glims_time_kernel", "glims_launch_count", "glims_cell_fields",
     "glims_nccl_unique_id", "glims_comm_init", "glims_set_halo", "glims_tile_info", "glims_tile_config", "glims_set_p2p", "glims_comm_bench",
-    "glims_prepare", "glims_reset_history", "glims_project_fields", "glims_mass_solve", "glims_set_dof_permutation", "glims_get_dof_permutation",
+    "glims_prepare", "glims_reset_history", "glims_project_fields", "glims_mass_solve", "glims_adjoint", "glims_set_dof_permutation", "glims_get_dof_permutation",
 ]
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOT_CONVERGED, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5
@@ -97,6 +97,7 @@ def load():
         "glims_prepare": (i32, [p, C.POINTER(SolverOpts)]),
         "glims_project_fields": (i32, [p, dp]),
         "glims_mass_solve": (i32, [p, i32, dp, dp]),
+        "glims_adjoint": (i32, [p, i32, C.POINTER(SolverOpts), i32, dp, dp, dp, C.POINTER(C.c_double), dp]),
         "glims_reset_history": (i32, [p]),
         "glims_set_dof_permutation": (i32, [p, lp]),
         "glims_get_dof_permutation": (i32, [p, lp]),

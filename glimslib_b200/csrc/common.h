@@ -222,6 +222,14 @@ void launch_scalar_diag_inverse(glims_ctx* c, const double* A, double* out);
 void flush_l2(glims_ctx* c);
 void launch_permute(glims_ctx* c, const double* src, double* dst, const i64* perm, i64 n, bool scatter);  // scatter: dst[perm[i]] = src[i]
 
+// ---------------- adjoint.cu (kernels of the discrete adjoint; the driver is glims_adjoint in solver.cu)
+void launch_spmv_uc_T(glims_ctx* c, const double* lu, double* out);                       // out[n_v] = K_uc^T l_u
+void launch_adjoint_grad(glims_ctx* c, const double* x, const double* lu, const double* lc, double* grad);   // grad[n_mat][3] +=
+void launch_threshold(glims_ctx* c, const double* cvec, const double* tgt, double level, double* r, double* dth);
+void launch_acc_prod(glims_ctx* c, double* g, int sg, int og, double s, const double* a, const double* b, i64 n);
+void launch_diff_strided(glims_ctx* c, const double* a, const double* b, int stride, int off, i64 n, double* r);
+void launch_zero_bc_split(glims_ctx* c, double* ru, double* rc);
+
 // ---------------- amg.cu
 void amg_setup(glims_ctx* c);
 void amg_free(glims_ctx* c);

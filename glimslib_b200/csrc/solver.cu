@@ -1110,6 +1110,105 @@ int glims_mass_solve(glims_ctx* c, int32_t nf, const double* load, double* out) 
     API_END
 }
 
+int glims_adjoint(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, int32_t n_levels, const double* levels,
+                  const double* level_targets, const double* u_target, double* J_out, double* grad) {
+    API_BEGIN
+    if (!c->have_mat) throw GlError(GLIMS_ERR_STATE, "glims_adjoint before glims_set_materials");
+    if (n_steps <= 0 || n_levels < 0 || (n_levels > 0 && (!levels || !level_targets)) || !J_out || !grad)
+        throw GlError(GLIMS_ERR_ARG, "glims_adjoint: bad arguments");
+    if (c->halo.active) throw GlError(GLIMS_ERR_STATE, "glims_adjoint: one GPU only (the adjoint sweep is not partitioned yet)");
+    if (c->dof_perm) throw GlError(GLIMS_ERR_STATE, "glims_adjoint: not available with a caller dof permutation");
+    glims_solver_opts od;
+    if (!o) { glims_default_opts(&od); o = &od; }
+    if (o->solver != GLIMS_SOLVER_BLOCK_TRI) throw GlError(GLIMS_ERR_ARG, "glims_adjoint: needs the block-triangular solver");
+    if (!cc_available(c)) throw GlError(GLIMS_ERR_STATE, std::string("glims_adjoint: row-walk maps unavailable: ") + cc_status(c));
+    const int D = c->dim, NB = c->nb;
+    const i64 nv = c->n_v, nr = nrows(c), nd = c->ndof;
+    // ---- forward sweep, trajectory on the device ------------------------------------------------------------------
+    double* traj = ws(c, "adj_traj", (i64)(n_steps + 1) * nd);
+    launch_copy(c, c->xprev, traj, nd);
+    for (int s = 0; s < n_steps; ++s) {
+        newton_step(c, o, nullptr);
+        launch_copy(c, c->x, c->xprev, nd);
+        launch_copy(c, c->x, traj + (i64)(s + 1) * nd, nd);
+    }
+    c->have_hist = false;
+    // ---- misfit of the final state and -dJ/dx_N ---------------------------------------------------------------------
+    double *xu = ws(c, "adj_xu", nv * D), *xc = ws(c, "adj_xc", nv), *ru = ws(c, "adj_ru", nv * D), *rc = ws(c, "adj_rc", nv);
+    double *r = ws(c, "adj_r", nv), *dth = ws(c, "adj_dth", nv), *Mr = ws(c, "adj_Mr", nv), *tg = ws(c, "adj_tg", nv * std::max(D, 1));
+    double *lu = ws(c, "adj_lu", nv * D), *lc = ws(c, "adj_lc", nv), *tmpc = ws(c, "adj_tmpc", nv);
+    double* dgrad = ws(c, "adj_grad", MAX_MAT * 3);
+    launch_extract(c, c->x, xu, xc);
+    launch_zero(c, ru, nv * D);
+    launch_zero(c, rc, nv);
+    double J = 0.0;
+    (void)cc_mass_matrix(c);         // builds the mass matrix on first use
+    for (int l = 0; l < n_levels; ++l) {
+        GL_CUDA(cudaMemcpyAsync(tg, level_targets + (i64)l * nv, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+        launch_threshold(c, xc, tg, levels[l], r, dth);
+        launch_spmv(c, 3, r, Mr);
+        launch_dot(c, r, Mr, nr, S_TMP0);
+        double v; read_scalars(c, S_TMP0, 1, &v);
+        J += v;
+        launch_acc_prod(c, rc, 1, 0, -2.0, Mr, dth, nr);            // rhs_c = -dJ/dc
+    }
+    if (u_target) {
+        GL_CUDA(cudaMemcpyAsync(tg, u_target, sizeof(double) * nv * D, cudaMemcpyHostToDevice, c->stream));
+        for (int k = 0; k < D; ++k) {
+            launch_diff_strided(c, xu, tg, D, k, nr, r);
+            launch_spmv(c, 3, r, Mr);
+            launch_dot(c, r, Mr, nr, S_TMP0);
+            double v; read_scalars(c, S_TMP0, 1, &v);
+            J += v;
+            launch_acc_prod(c, ru, D, k, -2.0, Mr, nullptr, nr);    // rhs_u = -dJ/du
+        }
+    }
+    *J_out = J;
+    // ---- adjoint sweep ------------------------------------------------------------------------------------------------
+    GL_CUDA(cudaMemsetAsync(dgrad, 0, sizeof(double) * MAX_MAT * 3, c->stream));
+    ensure_kconst(c, o);
+    for (int n = n_steps; n >= 1; --n) {
+        // state of step n: K_cc(c_n), Dirichlet-eliminated like the forward solves
+        launch_copy(c, traj + (i64)n * nd, c->x, nd);
+        launch_cc_rows(c, true, false);
+        launch_bc_matrix(c, GLIMS_ASM_KCC, true);
+        launch_diag_inverse(c, 2);
+        launch_zero_bc_split(c, ru, rc);
+        // K_uu l_u = rhs_u
+        double res = 0;
+        launch_dot(c, ru, ru, nr * D, S_TMP0);
+        double bu2; read_scalars(c, S_TMP0, 1, &bu2);
+        if (bu2 > 0.0) {
+            int its = pcg(c, 1, o->pc, ru, lu, o->ksp_rtol, 0.0, o->ksp_atol, o->max_krylov, &res, false);
+            if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "glims_adjoint: K_uu solve did not converge");
+        } else launch_zero(c, lu, nv * D);
+        // K_cc l_c = rhs_c - K_uc^T l_u
+        launch_spmv_uc_T(c, lu, tmpc);
+        launch_axpy(c, -1.0, tmpc, rc, nr);
+        launch_zero_bc_split(c, ru, rc);
+        launch_dot(c, rc, rc, nr, S_TMP0);
+        double bc2; read_scalars(c, S_TMP0, 1, &bc2);
+        if (bc2 > 0.0) {
+            int its = pcg(c, 2, GLIMS_PC_JACOBI, rc, lc, o->ksp_rtol, 0.0, o->ksp_atol, o->max_krylov, &res);
+            if (its < 0) throw GlError(GLIMS_ERR_NOT_CONVERGED, "glims_adjoint: K_cc solve did not converge");
+        } else launch_zero(c, lc, nv);
+        // gradient contributions of step n
+        launch_adjoint_grad(c, c->x, lu, lc, dgrad);
+        // rhs of step n-1: -(dR_n/dx_{n-1})^T l_n = M l_c on the concentration rows, nothing on the displacement rows
+        launch_spmv(c, 3, lc, rc);
+        launch_zero(c, ru, nv * D);
+    }
+    std::vector<double> hg(MAX_MAT * 3);
+    GL_CUDA(cudaMemcpyAsync(hg.data(), dgrad, sizeof(double) * MAX_MAT * 3, cudaMemcpyDeviceToHost, c->stream));
+    // leave the context at the end of the forward run
+    launch_copy(c, traj + (i64)n_steps * nd, c->x, nd);
+    launch_copy(c, c->x, c->xprev, nd);
+    GL_CUDA(cudaStreamSynchronize(c->stream));
+    for (int m = 0; m < c->n_mat * 3; ++m) grad[m] = hg[m];
+    c->fu_cache_valid = false;
+    API_END
+}
+
 int glims_tile_config(glims_ctx* c, int32_t threads_per_cta, int32_t chunk) {
     API_BEGIN
     if (threads_per_cta != 0 && threads_per_cta != 128 && threads_per_cta != 192 && threads_per_cta != 256)

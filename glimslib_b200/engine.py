@@ -89,6 +89,7 @@ class Engine:
         if t.ndim != 2 or t.shape[1] != 5:
             raise ValueError("material table must be (n_mat, 5): mu, lambda, D, rho, gamma")
         self._check(self._lib.glims_set_materials(self._h, len(t), N.as_dp(t)), "set_materials")
+        self._n_mat = len(t)
 
     def set_dt(self, dt):
         self._check(self._lib.glims_set_dt(self._h, float(dt)), "set_dt")
@@ -259,6 +260,25 @@ class Engine:
         out = np.empty_like(a)
         self._check(self._lib.glims_mass_solve(self._h, a.shape[1], N.as_dp(a), N.as_dp(out)), "mass_solve")
         return out[self._new_of_old] if self._new_of_old is not None else out
+
+    def adjoint_gradient(self, n_steps, levels=(), level_targets=None, u_target=None, **opts):
+        """Forward ``n_steps`` from the current (prev, state) and the discrete-adjoint gradient of the final-state misfit
+        (``glims_adjoint``).  Returns ``(J, grad)`` with ``grad[m] = (dJ/dD_m, dJ/drho_m, dJ/dgamma_m)`` per material row."""
+        for k, v in opts.items():
+            setattr(self.opts, k, v)
+        if self._new_of_old is not None:
+            raise EngineError("adjoint_gradient: not available on a reordered engine")
+        lev = N.f64(np.atleast_1d(np.asarray(levels, dtype=np.float64)))
+        nl = len(lev) if len(levels) else 0
+        tg = N.f64(level_targets).reshape(nl, self.n_vertices) if nl else np.zeros((1, 1))
+        ut = None if u_target is None else N.f64(u_target).reshape(self.n_vertices, self.dim)
+        n_mat = int(self._n_mat)
+        J = C.c_double()
+        grad = np.zeros((n_mat, 3))
+        rc = self._lib.glims_adjoint(self._h, int(n_steps), C.byref(self.opts), nl, N.as_dp(lev) if nl else None,
+                                     N.as_dp(tg) if nl else None, N.as_dp(ut) if ut is not None else None, C.byref(J), N.as_dp(grad))
+        self._check(rc, "adjoint")
+        return float(J.value), grad
 
     def time_kernel(self, kernel, variant=0, reps=10, flush_l2=True):
         ms = C.c_float()

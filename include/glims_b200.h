@@ -194,6 +194,17 @@ int glims_project_fields(glims_ctx* c, double* vertex_out);
    mass matrix of the mesh -- the linear solve inside every `fenics.project(expr, V)` of the reference's post-processing
    (helper_classes.py:1566-1618); the caller integrates `expr` against the hat functions. */
 int glims_mass_solve(glims_ctx* c, int32_t nf, const double* load, double* out);
+/* Discrete adjoint of the time loop (the reference's production caller: image_based_optimization.py:660-767 differentiates
+   a misfit of the final state with dolfin-adjoint w.r.t. the controls of run_for_adjoint,
+   simulation_tumor_growth_brain.py:127-145).  Runs n_steps forward steps from the current (prev, state) keeping the
+   trajectory on the device, evaluates
+       J = sum_l (th_l(c_N) - t_l)^T M (th_l(c_N) - t_l) + (u_N - u_t)^T (M x I) (u_N - u_t),
+   th_l(c) = 0.5 (tanh((c - level_l)/0.01) + 1)  (:1404-1407), M the P1 mass matrix, and returns J and
+   grad[n_mat][3] = dJ/d(D_m), dJ/d(rho_m), dJ/d(gamma_m) for every material row by one backward sweep of transposed block
+   solves (K_uu with the forward AMG hierarchy, then K_cc).  level_targets[n_levels][n_vertices], u_target[n_vertices][dim]
+   (NULL: no displacement term).  One GPU, block-triangular solver. */
+int glims_adjoint(glims_ctx* c, int32_t n_steps, const glims_solver_opts* o, int32_t n_levels, const double* levels,
+                  const double* level_targets, const double* u_target, double* J_out, double* grad);
 /* Tile-assembly map statistics (after the first GLIMS_ASMK_TILE assembly): info[0..7] = max local vertices, max element
    records, max contributor entries, max items, max partial buffers per slice, shared-memory bytes per CTA, device bytes of
    the maps, threads per CTA.  Returns GLIMS_ERR_STATE when the maps were not built or cannot represent the mesh. */
