@@ -1205,6 +1205,9 @@ void amg_setup(glims_ctx* c) {
     {
         Level& l = amg->L.back();
         const int bs = l.bs, n = l.n, m = n * bs;
+        // aggregation that stalls on a large level must not end in an O(m^2) dense inverse: fail loudly
+        if (m > 8192) throw GlError(GLIMS_ERR_STATE, "amg: coarsening stalled at " + std::to_string(n) + " nodes on level " + std::to_string(amg->L.size() - 1) +
+                                                     "; use GLIMS_PC_JACOBI for this mesh");
         amg->coarse_m = m;
         HostGraph g = download_graph(l.pat);
         std::vector<double> Av((i64)l.pat.n_slots * bs * bs);

@@ -556,6 +556,9 @@ int glims_comm_init(glims_ctx* c, int32_t n_ranks, int32_t rank, const void* id1
         ncclComm_t comm;
         GL_NCCL(ncclCommInitRank(&comm, n_ranks, id, rank));
         c->halo.comm = comm; c->halo.n_ranks = n_ranks; c->halo.rank = rank;
+        // every rank of a multi-rank run takes part in every collective, also one whose share happens to have no ghost
+        // vertices (it would otherwise skip the allreduces and leave the others waiting)
+        if (n_ranks > 1 && !c->halo.active) { c->halo.active = true; c->halo.n_owned = c->n_v; }
         if (c->halo.send_idx) p2p_setup(c);      // halo plan known (glims_set_halo comes first): map the peer windows
     } catch (const GlError& e) { c->err = e.msg; return e.code; }
     return GLIMS_OK;
