@@ -499,8 +499,97 @@ __global__ void k_to_double(const float* __restrict__ a, double* __restrict__ b,
 __device__ inline float ld_mat(const float* p) { return __ldcs(p); }
 __device__ inline float ld_mat(const __half* p) { return __half2float(__ldcs(p)); }
 
-// thread per block row (fine level, BS = 2|3): y = A x  or  y = rhs - A x.  MT = float, or __half with the values
-// scaled by a power of two (unscale restores the row sums; FP32 accumulation either way)
+// Fine-level FP16 matrix, slot-pair layout.  Slots 2q and 2q+1 of a slice are interleaved as __half2 -- entry k of both blocks
+// for the 32 rows of the slice is one 128-byte line, [q][k][lane] -- and an odd last slot keeps the scalar [k][lane] form, so the
+// array has exactly the size and slice offsets of the scalar layout.  A block pair then costs BS*BS 4-byte loads per lane
+// instead of 2*BS*BS 2-byte ones (64-byte warp requests), and the column indices of the next pair are fetched before the
+// gathers of the current one are consumed: twice the bytes in flight per warp for a kernel that waits on the long scoreboard
+// 64 cycles per issue (profiles/r02_ncu_summary.md).
+template <int BSQ>
+__global__ void k_to_half_paired(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, int n_slices,
+                                 const double* __restrict__ A, __half* __restrict__ A16, double scale) {
+    for (int S = blockIdx.x; S < n_slices; S += gridDim.x) {
+        const i64 base = slice_off[S] * BSQ;
+        const int w = slice_w[S], np = w >> 1, n = w * BSQ * 32;
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const int j = t / (BSQ * 32), rem = t - j * (BSQ * 32);
+            const i64 dst = j < 2 * np ? base + (i64)(j >> 1) * (2 * BSQ * 32) + rem * 2 + (j & 1) : base + t;
+            A16[dst] = __double2half(A[base + t] * scale);
+        }
+    }
+}
+
+// matrix stream: read once, keep it out of L1 (which then holds the gathered x blocks)
+__device__ inline __half2 ld_stream_h2(const __half2* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return *reinterpret_cast<__half2*>(&v);
+}
+template <int BS>
+__device__ inline void row_dot(const i64 base, const int w, const int* __restrict__ col, const __half* __restrict__ A,
+                               const float* __restrict__ x, const int lane, float (&acc)[BS]) {
+    constexpr int BSQ = BS * BS;
+    const int np = w >> 1;
+    const __half2* Ap = reinterpret_cast<const __half2*>(A + base * BSQ) + lane;
+    const int* cp = col + base + lane;
+    // software pipeline: the matrix pair and the column indices of step q+1 are requested before the gathers of step q are used
+    int c0 = 0, c1 = 0;
+    __half2 an[BSQ];
+    if (np > 0) {
+        c0 = __ldg(cp); c1 = __ldg(cp + 32);
+#pragma unroll
+        for (int k = 0; k < BSQ; ++k) an[k] = ld_stream_h2(&Ap[k * 32]);
+    }
+    for (int q = 0; q < np; ++q) {
+        float x0[BS], x1[BS];
+#pragma unroll
+        for (int b = 0; b < BS; ++b) { x0[b] = __ldg(&x[(i64)c0 * BS + b]); x1[b] = __ldg(&x[(i64)c1 * BS + b]); }
+        __half2 a[BSQ];
+#pragma unroll
+        for (int k = 0; k < BSQ; ++k) a[k] = an[k];
+        if (q + 1 < np) {
+            c0 = __ldg(cp + (2 * q + 2) * 32); c1 = __ldg(cp + (2 * q + 3) * 32);
+            const __half2* Aq = Ap + (i64)(q + 1) * (BSQ * 32);
+#pragma unroll
+            for (int k = 0; k < BSQ; ++k) an[k] = ld_stream_h2(&Aq[k * 32]);
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int b = 0; b < BS; ++b) {
+                const float2 f = __half22float2(a[i * BS + b]);
+                acc[i] = fmaf(f.x, x0[b], acc[i]); acc[i] = fmaf(f.y, x1[b], acc[i]);
+            }
+    }
+    if (w & 1) {
+        const i64 g = base + (i64)(w - 1) * 32;
+        const int cidx = __ldg(&col[g + lane]);
+        const __half* Ag = A + g * BSQ + lane;
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc[i] = fmaf(__half2float(__ldcs(&Ag[(i * BS + b) * 32])), __ldg(&x[(i64)cidx * BS + b]), acc[i]);
+    }
+}
+template <int BS>
+__device__ inline void row_dot(const i64 base, const int w, const int* __restrict__ col, const float* __restrict__ A,
+                               const float* __restrict__ x, const int lane, float (&acc)[BS]) {
+    for (int j = 0; j < w; ++j) {
+        const i64 g = base + (i64)j * 32;
+        const int cidx = __ldg(&col[g + lane]);
+        float xv[BS];
+#pragma unroll
+        for (int b = 0; b < BS; ++b) xv[b] = __ldg(&x[(i64)cidx * BS + b]);
+        const float* Ag = A + g * (BS * BS) + lane;
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc[i] += ld_mat(&Ag[(i * BS + b) * 32]) * xv[b];
+    }
+}
+
+// thread per block row (fine level, BS = 2|3): y = A x  or  y = rhs - A x.  MT = float, or __half (slot-pair layout) with the
+// values scaled by a power of two (unscale restores the row sums; FP32 accumulation either way)
 template <int BS, bool RESID, typename MT>
 __global__ void __launch_bounds__(TPB)
 k_spmv32_row(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
@@ -514,20 +603,7 @@ k_spmv32_row(const i64* __restrict__ slice_off, const int* __restrict__ slice_w,
         float acc[BS];
 #pragma unroll
         for (int i = 0; i < BS; ++i) acc[i] = 0.f;
-        const i64 base = slice_off[S];
-        const int w = slice_w[S];
-        for (int j = 0; j < w; ++j) {
-            const i64 g = base + (i64)j * 32;
-            const int cidx = __ldg(&col[g + lane]);
-            float xv[BS];
-#pragma unroll
-            for (int b = 0; b < BS; ++b) xv[b] = __ldg(&x[(i64)cidx * BS + b]);
-            const MT* Ag = A + g * (BS * BS) + lane;
-#pragma unroll
-            for (int i = 0; i < BS; ++i)
-#pragma unroll
-                for (int b = 0; b < BS; ++b) acc[i] += ld_mat(&Ag[(i * BS + b) * 32]) * xv[b];
-        }
+        row_dot<BS>(slice_off[S], slice_w[S], col, A, x, lane, acc);
         if (r < n_rows) {
 #pragma unroll
             for (int i = 0; i < BS; ++i) y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - unscale * acc[i] : unscale * acc[i];
@@ -621,20 +697,7 @@ k_spmv32_row_cheb(const i64* __restrict__ slice_off, const int* __restrict__ sli
         float acc[BS];
 #pragma unroll
         for (int i = 0; i < BS; ++i) acc[i] = 0.f;
-        const i64 base = slice_off[S];
-        const int w = slice_w[S];
-        for (int j = 0; j < w; ++j) {
-            const i64 g = base + (i64)j * 32;
-            const int cidx = __ldg(&col[g + lane]);
-            float xv[BS];
-#pragma unroll
-            for (int b = 0; b < BS; ++b) xv[b] = __ldg(&x[(i64)cidx * BS + b]);
-            const MT* Ag = A + g * (BS * BS) + lane;
-#pragma unroll
-            for (int i = 0; i < BS; ++i)
-#pragma unroll
-                for (int b = 0; b < BS; ++b) acc[i] += ld_mat(&Ag[(i * BS + b) * 32]) * xv[b];
-        }
+        row_dot<BS>(slice_off[S], slice_w[S], col, A, x, lane, acc);
         if (r < n_rows) {
             float rv[BS];
 #pragma unroll
@@ -784,7 +847,9 @@ void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) 
         }
 #undef SPLIT_GO
     } else {
-        int g = sgrid(p.n_rows);
+        // one 256-row tile per CTA: the hardware scheduler balances tiles of different widths, and the grid does not depend on
+        // how many CTAs the register count lets an SM hold (a capped grid of 8 per SM ran a second, thin wave at 6 resident)
+        int g = (p.n_rows + TPB - 1) / TPB;
         if (l.A16) {
             const float us = l.a16_unscale;
             if (l.bs == 2) {
@@ -817,7 +882,9 @@ void cheb_step32(glims_ctx* c, Level& l, const float* b, const float* x, float* 
         else { if (l.bs == 6) SPLITC_GO(6, float, l.A32, 1.f); else SPLITC_GO(3, float, l.A32, 1.f); }
 #undef SPLITC_GO
     } else {
-        int g = sgrid(p.n_rows);
+        // one 256-row tile per CTA: the hardware scheduler balances tiles of different widths, and the grid does not depend on
+        // how many CTAs the register count lets an SM hold (a capped grid of 8 per SM ran a second, thin wave at 6 resident)
+        int g = (p.n_rows + TPB - 1) / TPB;
         if (l.A16) {
             if (l.bs == 2) k_spmv32_row_cheb<2, __half><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A16, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2, l.a16_unscale);
             else k_spmv32_row_cheb<3, __half><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, l.A16, x, xn, p.n_rows, b, l.dinv32, l.d32, c1, c2, l.a16_unscale);
@@ -953,7 +1020,9 @@ void build_fp32(glims_ctx* c, Amg* amg) {
             if (amax > 0) { std::frexp(amax, &ex); }
             const double scale = std::ldexp(1.0, 14 - ex);       // largest magnitude lands in [2^13, 2^14)
             GL_CUDA(cudaMalloc(&l.A16, sizeof(__half) * na));
-            k_to_half<<<sgrid(na), TPB, 0, c->stream>>>(l.A, l.A16, na, scale);
+            if (l.owns_A) k_to_half<<<sgrid(na), TPB, 0, c->stream>>>(l.A, l.A16, na, scale);          // split kernels: scalar layout
+            else if (l.bs == 2) k_to_half_paired<4><<<148 * 8, TPB, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.n_slices, l.A, l.A16, scale);
+            else k_to_half_paired<9><<<148 * 8, TPB, 0, c->stream>>>(l.pat.slice_off, l.pat.slice_w, l.pat.n_slices, l.A, l.A16, scale);
             l.a16_unscale = (float)(1.0 / scale);
         } else {
             GL_CUDA(cudaMalloc(&l.A32, sizeof(float) * std::max<i64>(na, 1)));

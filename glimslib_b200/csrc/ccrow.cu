@@ -589,7 +589,7 @@ bool launch_cc_rows(glims_ctx* c, bool with_kcc, bool with_res) {
 static void fu_launch(glims_ctx* c, const double* x, const double* lift, const double* fext, double* out, int stride) {
     const auto& p = c->pat;
     i64 need = (p.n_rows + 255) / 256;
-    const int g = (int)std::max<i64>(1, std::min<i64>(need, 148 * 8));
+    const int g = c->dim == 2 ? fit_grid(k_fu<2>, need, 256, 148 * 8) : fit_grid(k_fu<3>, need, 256, 148 * 8);
     if (c->dim == 2) k_fu<2><<<g, 256, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, x, p.n_rows, lift, fext, out, stride);
     else k_fu<3><<<g, 256, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, x, p.n_rows, lift, fext, out, stride);
     c->launches++;

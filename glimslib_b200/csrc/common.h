@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "../../include/glims_b200.h"
 
@@ -25,6 +27,31 @@ struct GlError {
     std::string msg;
     GlError(int c, const std::string& m) : code(c), msg(m) {}
 };
+
+// Grid of a grid-stride kernel = what the device holds at once (resident CTAs per SM x SMs), from the occupancy calculator and
+// cached per kernel.  A fixed 8-per-SM grid runs a second, thin wave for every kernel that needs more than 32 registers
+// (6 resident CTAs of 256 threads at 40): the fine-level smoother step lost 16 % to that tail.
+inline int resident_grid(const void* kernel, int threads, size_t dyn_smem = 0) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(kernel);
+    if (it != cache.end()) return it->second;
+    int per_sm = 0, dev = 0, sms = 148;
+    GL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem));
+    GL_CUDA(cudaGetDevice(&dev));
+    GL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int g = (per_sm > 0 ? per_sm : 1) * sms;
+    cache[kernel] = g;
+    return g;
+}
+template <typename K>
+inline int fit_grid(K kernel, i64 tiles, int threads, int cap) {
+    i64 g = resident_grid((const void*)kernel, threads);
+    if (g > cap) g = cap;
+    if (g > tiles) g = tiles;
+    return (int)(g > 0 ? g : 1);
+}
 
 constexpr int SLICE = 32;          // SELL-32: one warp lane per block row
 constexpr int MAX_MAT = 64;        // material table rows staged in shared memory

@@ -1141,24 +1141,21 @@ void launch_export_values(glims_ctx* c, double* Kuu, double* Kuc, double* Kcc) {
 
 void launch_spmv(glims_ctx* c, int which, const double* x, double* y, SpmvDot dot) {
     auto& p = c->pat;
-    int g = red_grid(c, p.n_rows);
+    const i64 tiles = (p.n_rows + TPB - 1) / TPB;
     bool d = dot.w != nullptr;
 #define ARGS p.n_rows, dot.w, c->partials, c->tickets, c->scal, dot.slot
+#define GO(K, ...) K<<<fit_grid(K, tiles, TPB, MAXBLK), TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, __VA_ARGS__, x, y, ARGS)
     if (which == 0) {
-        if (c->dim == 2) { if (d) k_spmv_mono<2, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, c->Kcc, x, y, ARGS);
-                           else k_spmv_mono<2, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, c->Kcc, x, y, ARGS); }
-        else             { if (d) k_spmv_mono<3, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, c->Kcc, x, y, ARGS);
-                           else k_spmv_mono<3, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, c->Kuc, c->Kcc, x, y, ARGS); }
+        if (c->dim == 2) { if (d) GO((k_spmv_mono<2, true>), c->Kuu, c->Kuc, c->Kcc); else GO((k_spmv_mono<2, false>), c->Kuu, c->Kuc, c->Kcc); }
+        else             { if (d) GO((k_spmv_mono<3, true>), c->Kuu, c->Kuc, c->Kcc); else GO((k_spmv_mono<3, false>), c->Kuu, c->Kuc, c->Kcc); }
     } else if (which == 1) {
-        if (c->dim == 2) { if (d) k_spmv_block<2, 2, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS);
-                           else k_spmv_block<2, 2, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS); }
-        else             { if (d) k_spmv_block<3, 3, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS);
-                           else k_spmv_block<3, 3, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, c->Kuu, x, y, ARGS); }
+        if (c->dim == 2) { if (d) GO((k_spmv_block<2, 2, true>), c->Kuu); else GO((k_spmv_block<2, 2, false>), c->Kuu); }
+        else             { if (d) GO((k_spmv_block<3, 3, true>), c->Kuu); else GO((k_spmv_block<3, 3, false>), c->Kuu); }
     } else {
         const double* A = which == 3 ? cc_mass_matrix(c) : c->Kcc;      // 3: the P1 mass matrix (L2 projections)
-        if (d) k_spmv_block<1, 1, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, ARGS);
-        else k_spmv_block<1, 1, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, ARGS);
+        if (d) GO((k_spmv_block<1, 1, true>), A); else GO((k_spmv_block<1, 1, false>), A);
     }
+#undef GO
 #undef ARGS
     LAUNCHED(c);
 }
@@ -1179,9 +1176,9 @@ void launch_spmv_generic(glims_ctx* c, const SellPattern& p, const double* A, in
         LAUNCHED(c);
         return;
     }
-    int g = red_grid(c, p.n_rows);
-#define GEN(B) do { if (rhs) k_spmv_block<B, B, false, true><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, rhs, c->partials, c->tickets, c->scal, 0); \
-                    else k_spmv_block<B, B, false, false><<<g, TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, nullptr, c->partials, c->tickets, c->scal, 0); } while (0)
+    const i64 tiles = (p.n_rows + TPB - 1) / TPB;
+#define GEN(B) do { if (rhs) k_spmv_block<B, B, false, true><<<fit_grid(k_spmv_block<B, B, false, true>, tiles, TPB, MAXBLK), TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, rhs, c->partials, c->tickets, c->scal, 0); \
+                    else k_spmv_block<B, B, false, false><<<fit_grid(k_spmv_block<B, B, false, false>, tiles, TPB, MAXBLK), TPB, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, y, p.n_rows, nullptr, c->partials, c->tickets, c->scal, 0); } while (0)
     if (bs == 1) GEN(1); else if (bs == 2) GEN(2); else if (bs == 3) GEN(3);
     else throw GlError(GLIMS_ERR_ARG, "spmv_generic: unsupported block size");
 #undef GEN
