@@ -8,6 +8,7 @@
 // Fully constrained (Dirichlet) vertices and ghost vertices are left out of the coarse space, so on a
 // partitioned mesh the preconditioner is rank-local (block-Jacobi over sub-domains) with no communication.
 #include "common.h"
+#include "tma.cuh"
 #include <cuda_fp16.h>
 #include <thrust/device_ptr.h>
 #include <thrust/device_vector.h>
@@ -386,6 +387,37 @@ int aggregate(const HostGraph& g, int n, const std::vector<char>& excluded, std:
     return na;
 }
 
+// Renumber the aggregates so that coarse rows of similar length share a SELL slice: within windows of `window` consecutive
+// aggregates (the sweep order of `aggregate` is spatially coherent, so a window keeps the gather locality) sort by the number of
+// distinct neighbouring aggregates.  At C4 the level-1 operator carried 23 % padding slots (1.30 M blocks in 1.59 M slots), all
+// of them streamed by four passes per V-cycle.  GLIMS_AMG_SORT=<window> enables it (default off, see the call site).
+void relabel_by_degree(const HostGraph& g, int n, std::vector<int>& agg, int na, int window) {
+    if (na <= 32) return;
+    std::vector<int> mptr(na + 1, 0), midx;
+    for (int i = 0; i < n; ++i) if (agg[i] >= 0) mptr[agg[i] + 1]++;
+    for (int I = 0; I < na; ++I) mptr[I + 1] += mptr[I];
+    midx.resize(mptr[na]);
+    { std::vector<int> pos(mptr.begin(), mptr.end() - 1); for (int i = 0; i < n; ++i) if (agg[i] >= 0) midx[pos[agg[i]]++] = i; }
+    std::vector<int> deg(na, 0), mark(na, -1);
+    for (int I = 0; I < na; ++I)
+        for (int t = mptr[I]; t < mptr[I + 1]; ++t) {
+            const int i = midx[t];
+            for (i64 e = g.rowptr[i]; e < g.rowptr[i + 1]; ++e) {
+                const int j = g.col[e];
+                if (j >= n || agg[j] < 0) continue;
+                if (mark[agg[j]] != I) { mark[agg[j]] = I; deg[I]++; }
+            }
+        }
+    std::vector<int> order(na), newid(na);
+    for (int I = 0; I < na; ++I) order[I] = I;
+    for (int w0 = 0; w0 < na; w0 += window) {
+        const int w1 = std::min(na, w0 + window);
+        std::stable_sort(order.begin() + w0, order.begin() + w1, [&](int a, int b) { return deg[a] > deg[b]; });
+    }
+    for (int k = 0; k < na; ++k) newid[order[k]] = k;
+    for (int i = 0; i < n; ++i) if (agg[i] >= 0) agg[i] = newid[agg[i]];
+}
+
 void alloc_work(Level& l) {
     i64 n = std::max<i64>(l.n_cols, l.n) * l.bs;
     for (double** v : {&l.x, &l.b, &l.r, &l.d}) {
@@ -641,22 +673,71 @@ __device__ inline float split_row_dot(const i64 base, const int w, const int* __
     return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
+// The same product with the gathered x blocks staged in shared memory.  In the form above each of the BS component warps of a
+// slice gathers all BS components of every column block itself: BS*BS scattered 4-byte gathers per slot and CTA, and on level 1
+// (2 MB vector, 230 MB matrix per pass) the L1 tag stage of those gathers, not HBM, set the pace -- an FP16 matrix (half the
+// bytes) and a degree-sorted numbering (23 % fewer slots) both left the pass at 75-82 us.  Here warp i fetches the column index
+// and the whole x block of slots i, i+BS, ... once (8-byte loads when the block is 24 bytes) into xs[slot][component][lane];
+// after one barrier every warp streams its BS matrix values per slot against shared memory: the scattered work drops by BS to
+// 2 BS, and the matrix loads no longer wait behind a column -> gather chain.
+constexpr int SPLIT_CH = 24;      // slots staged per round (level-1 slices are <= 23 wide at C4)
+template <int BS, typename MT>
+__device__ inline float split_row_dot_staged(float (*xs)[BS][32], const i64 base, const int w, const int* __restrict__ col,
+                                             const MT* __restrict__ A, const float* __restrict__ x, const int i, const int lane) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j0 = 0; j0 < w; j0 += SPLIT_CH) {
+        const int nj = min(SPLIT_CH, w - j0);
+        if (j0 > 0) __syncthreads();
+#pragma unroll 4
+        for (int j = i; j < nj; j += BS) {
+            const int cidx = __ldg(&col[base + (i64)(j0 + j) * 32 + lane]);
+            if constexpr (BS % 2 == 0) {
+                const float2* xp = reinterpret_cast<const float2*>(x + (i64)cidx * BS);
+#pragma unroll
+                for (int b = 0; b < BS / 2; ++b) { const float2 v = __ldg(&xp[b]); xs[j][2 * b][lane] = v.x; xs[j][2 * b + 1][lane] = v.y; }
+            } else {
+#pragma unroll
+                for (int b = 0; b < BS; ++b) xs[j][b][lane] = __ldg(&x[(i64)cidx * BS + b]);
+            }
+        }
+        __syncthreads();
+        const MT* Ab = A + (base + (i64)j0 * 32) * (BS * BS) + (i * BS) * 32 + lane;
+        int j = 0;
+        for (; j + 3 < nj; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const MT* Au = Ab + (i64)(j + u) * 32 * (BS * BS);
+#pragma unroll
+                for (int b = 0; b < BS; ++b) acc[u] += ld_mat(&Au[b * 32]) * xs[j + u][b][lane];
+            }
+        }
+        for (; j < nj; ++j) {
+            const MT* A0 = Ab + (i64)j * 32 * (BS * BS);
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc[0] += ld_mat(&A0[b * 32]) * xs[j][b][lane];
+        }
+    }
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
 // CTA per slice, warp per block-row component (coarse levels, BS = 3|6)
-template <int BS, bool RESID, typename MT>
+template <int BS, bool RESID, typename MT, bool STAGED>
 __global__ void __launch_bounds__(32 * BS)
 k_spmv32_split(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
                const MT* __restrict__ A, const float* __restrict__ x, float* __restrict__ y, int n_rows,
                int slice0, int n_slices, const float* __restrict__ rhs, float unscale) {
+    __shared__ float xs[STAGED ? SPLIT_CH : 1][BS][32];
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
     for (int S = slice0 + blockIdx.x; S < slice0 + n_slices; S += gridDim.x) {
         const int r = S * 32 + lane;
         const i64 base = slice_off[S];
         const int w = slice_w[S];
-        const float dotv = split_row_dot<BS, MT>(base, w, col, A, x, i, lane);
+        const float dotv = STAGED ? split_row_dot_staged<BS, MT>(xs, base, w, col, A, x, i, lane) : split_row_dot<BS, MT>(base, w, col, A, x, i, lane);
         if (r < n_rows) {
             const float v = unscale * dotv;
             y[(i64)r * BS + i] = RESID ? rhs[(i64)r * BS + i] - v : v;
         }
+        if (STAGED) __syncthreads();      // xs is free for the next slice
     }
 }
 
@@ -717,19 +798,20 @@ k_spmv32_row_cheb(const i64* __restrict__ slice_off, const int* __restrict__ sli
 
 // Same step for the coarse levels: CTA per slice, warp i computes component i of the slice's 32 block rows; the residual
 // block of a row is exchanged through shared memory so that every thread can apply its row of Dinv.
-template <int BS, typename MT>
+template <int BS, typename MT, bool STAGED>
 __global__ void __launch_bounds__(32 * BS)
 k_spmv32_split_cheb(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
                     const MT* __restrict__ A, const float* __restrict__ x, float* __restrict__ xn, int n_rows,
                     int slice0, int n_slices, const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d,
                     float c1, float c2, float unscale) {
     __shared__ float rs[BS][32];
+    __shared__ float xs[STAGED ? SPLIT_CH : 1][BS][32];
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
     for (int S = slice0 + blockIdx.x; S < slice0 + n_slices; S += gridDim.x) {
         const int r = S * 32 + lane;
         const i64 base = slice_off[S];
         const int w = slice_w[S];
-        const float dotv = split_row_dot<BS, MT>(base, w, col, A, x, i, lane);
+        const float dotv = STAGED ? split_row_dot_staged<BS, MT>(xs, base, w, col, A, x, i, lane) : split_row_dot<BS, MT>(base, w, col, A, x, i, lane);
         rs[i][lane] = r < n_rows ? rhs[(i64)r * BS + i] - unscale * dotv : 0.f;
         __syncthreads();
         if (r < n_rows) {
@@ -742,6 +824,163 @@ k_spmv32_split_cheb(const i64* __restrict__ slice_off, const int* __restrict__ s
         }
         __syncthreads();
     }
+}
+
+// ---- coarse-level products fed by the bulk-copy engine ---------------------------------------------------------------------
+// The staged kernels above are bound by their chain of dependent loads: a slice is slice_off -> column -> gather -> w/4 rounds of
+// matrix loads -> epilogue operands, about ten memory latencies, and level 1 of C4 is only 2625 slices -- two waves, each CTA
+// idle at the memory system for most of its life (45 % of HBM bandwidth, 62 cycles of long-scoreboard stall per issue).  The
+// matrix of a slice is one contiguous run (w slots x BS*BS*128 B), so here thread 0 hands it to the bulk-copy engine in chunks
+// of TMA_SL slots through a TMA_NST-deep ring of shared-memory stages (mbarrier complete_tx), the warps gather the x blocks
+// meanwhile, and the products read shared memory only.  Persistent CTAs (grid = resident CTAs); ~74 KB of matrix in flight per
+// CTA independent of what the warps wait for.
+template <int BS, int TMA_SL, int TMA_NST, int CH>
+constexpr size_t split_tma_smem() { return (size_t)TMA_NST * TMA_SL * BS * BS * 128 + (size_t)CH * BS * 128 + (size_t)BS * 128; }
+
+// MODE 0: y = A x, 1: y = rhs - A x, 2: Chebyshev step (xn = x + d_new, d_new = c1 d + c2 Dinv (rhs - A x))
+template <int BS, int MODE, int TMA_SL, int TMA_NST, int CH>
+__global__ void __launch_bounds__(32 * BS)
+k_split_tma(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col,
+            const float* __restrict__ A, const float* __restrict__ x, float* __restrict__ out, int n_rows, int slice0, int n_slices,
+            const float* __restrict__ rhs, const float* __restrict__ dinv, float* __restrict__ d, float c1, float c2) {
+    constexpr int BSQ = BS * BS;
+    constexpr unsigned SLOT_BYTES = BSQ * 128;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* As = reinterpret_cast<float*>(smem);                                                  // [NST][SL][BSQ][32]
+    float (*xs)[BS][32] = reinterpret_cast<float (*)[BS][32]>(smem + (size_t)TMA_NST * TMA_SL * SLOT_BYTES);      // [CH][BS][32]
+    float (*rs)[32] = reinterpret_cast<float (*)[32]>(smem + (size_t)TMA_NST * TMA_SL * SLOT_BYTES + (size_t)CH * BS * 128);
+    __shared__ unsigned long long full[TMA_NST];
+    const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
+    if (threadIdx.x == 0)
+        for (int st = 0; st < TMA_NST; ++st) mbar_init(&full[st], 1);
+    __syncthreads();
+    unsigned kc = 0;          // chunks consumed so far by this CTA: stage = kc % NST, parity = (kc / NST) & 1
+    const int S_end = slice0 + n_slices;
+    // producer cursor (thread 0): the CTA's chunks form one sequence over all of its slices; chunk number k lives in stage k % NST
+    // and is requested as soon as chunk k - NST has been consumed, across slice boundaries
+    int pS = slice0 + blockIdx.x, pq = 0, p_w = 0, p_nch = 0;
+    i64 p_base = 0;
+    unsigned pk = 0;
+    int S = slice0 + blockIdx.x, nx_S = S, nx_w = S < S_end ? slice_w[S] : 0;      // header of the slice after the one being consumed
+    i64 nx_base = S < S_end ? slice_off[S] : 0;
+    auto advance = [&]() {
+        if (pS >= S_end) return;
+        const unsigned st = pk % TMA_NST;
+        const unsigned bytes = (unsigned)min(TMA_SL, p_w - pq * TMA_SL) * SLOT_BYTES;
+        mbar_expect_tx(&full[st], bytes);
+        bulk_g2s(As + (size_t)st * TMA_SL * BSQ * 32, A + (p_base + (i64)pq * TMA_SL * 32) * BSQ, bytes, &full[st]);
+        ++pk;
+        if (++pq == p_nch) {
+            pS += gridDim.x; pq = 0;
+            while (pS < S_end) {          // skip empty slices
+                if (pS == nx_S) { p_base = nx_base; p_w = nx_w; }        // normally the slice whose header is already here
+                else { p_base = slice_off[pS]; p_w = slice_w[pS]; }
+                p_nch = (p_w + TMA_SL - 1) / TMA_SL;
+                if (p_nch > 0) break;
+                pS += gridDim.x;
+            }
+        }
+    };
+    if (threadIdx.x == 0) {
+        while (pS < S_end) {
+            if (pS == nx_S) { p_base = nx_base; p_w = nx_w; } else { p_base = slice_off[pS]; p_w = slice_w[pS]; }
+            p_nch = (p_w + TMA_SL - 1) / TMA_SL;
+            if (p_nch > 0) break;
+            pS += gridDim.x;
+        }
+        for (int q = 0; q < TMA_NST; ++q) advance();
+    }
+    for (; S < S_end; S += gridDim.x) {
+        const int r = S * 32 + lane;
+        const i64 base = nx_base;
+        const int w = nx_w;
+        nx_S = S + (int)gridDim.x;
+        if (nx_S < S_end) { nx_base = slice_off[nx_S]; nx_w = slice_w[nx_S]; }      // next slice's header, early
+        const int nch = (w + TMA_SL - 1) / TMA_SL;
+        // epilogue operands do not depend on the product: request them now
+        float rhs_v = 0.f, d_v = 0.f, x_v = 0.f;
+        if (MODE >= 1 && r < n_rows) rhs_v = rhs[(i64)r * BS + i];
+        if (MODE == 2 && r < n_rows) { d_v = c1 != 0.f ? d[(i64)r * BS + i] : 0.f; x_v = x[(i64)r * BS + i]; }
+        float acc[TMA_SL];
+#pragma unroll
+        for (int u = 0; u < TMA_SL; ++u) acc[u] = 0.f;
+        for (int q = 0; q < nch; ++q) {
+            const int j0 = q * TMA_SL, jx = j0 % CH;
+            if (jx == 0) {            // (re)fill xs: warp i stages the x blocks of slots j0 + i, j0 + i + BS, ...
+                const int nj = min(CH, w - j0);
+#pragma unroll 4
+                for (int j = i; j < nj; j += BS) {
+                    const int cidx = __ldg(&col[base + (i64)(j0 + j) * 32 + lane]);
+                    if constexpr (BS % 2 == 0) {
+                        const float2* xp = reinterpret_cast<const float2*>(x + (i64)cidx * BS);
+#pragma unroll
+                        for (int b = 0; b < BS / 2; ++b) { const float2 v = __ldg(&xp[b]); xs[j][2 * b][lane] = v.x; xs[j][2 * b + 1][lane] = v.y; }
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < BS; ++b) xs[j][b][lane] = __ldg(&x[(i64)cidx * BS + b]);
+                    }
+                }
+                __syncthreads();
+            }
+            const unsigned st = (kc + q) % TMA_NST;
+            mbar_wait(&full[st], ((kc + q) / TMA_NST) & 1u);
+            const int nsl = min(TMA_SL, w - j0);
+            const float* Ast = As + (size_t)st * TMA_SL * BSQ * 32 + (i * BS) * 32 + lane;
+#pragma unroll
+            for (int u = 0; u < TMA_SL; ++u)
+                if (u < nsl) {
+#pragma unroll
+                    for (int b = 0; b < BS; ++b) acc[u] += Ast[u * BSQ * 32 + b * 32] * xs[jx + u][b][lane];
+                }
+            __syncthreads();          // every warp is done with stage st (and, at the end of an xs round, with xs)
+            if (threadIdx.x == 0) advance();
+        }
+        kc += nch;
+        float dotv = 0.f;
+#pragma unroll
+        for (int u = 0; u < TMA_SL; ++u) dotv += acc[u];
+        if (MODE < 2) {
+            if (r < n_rows) out[(i64)r * BS + i] = MODE == 1 ? rhs_v - dotv : dotv;
+        } else {
+            rs[i][lane] = rhs_v - dotv;
+            __syncthreads();
+            if (r < n_rows) {
+                float z = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < BS; ++jj) z += dinv[(i64)r * BSQ + i * BS + jj] * rs[jj][lane];
+                const float dn = c2 * z + c1 * d_v;
+                d[(i64)r * BS + i] = dn;
+                out[(i64)r * BS + i] = x_v + dn;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int BS, int MODE, int SL, int NST, int CH>
+void launch_split_tma_cfg(glims_ctx* c, const SellPattern& p, const float* A, const float* x, float* out, int s0, int ns,
+                          const float* rhs, const float* dinv, float* d, float c1, float c2) {
+    constexpr size_t smem = split_tma_smem<BS, SL, NST, CH>();
+    static int grid_cap = 0;
+    if (!grid_cap) {
+        GL_CUDA(cudaFuncSetAttribute(k_split_tma<BS, MODE, SL, NST, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        grid_cap = resident_grid((const void*)k_split_tma<BS, MODE, SL, NST, CH>, 32 * BS, smem);
+    }
+    const int g = ns < grid_cap ? ns : grid_cap;
+    k_split_tma<BS, MODE, SL, NST, CH><<<g, 32 * BS, smem, c->stream>>>(p.slice_off, p.slice_w, p.col, A, x, out, p.n_rows, s0, ns, rhs, dinv, d, c1, c2);
+}
+// GLIMS_SPLIT_TMA: 0 off, else the ring shape (slots per chunk, stages, x slots staged): 1 = 4,3,24 (75 KB per CTA), 2 = 2,4,24 (56 KB),
+// 3 = 2,3,12 (38 KB, five CTAs per SM; default).  One level-1 smoother step at C4 / at an eighth of C4, L2 flushed: register-staged
+// kernel 75 / 37 us, shared-memory-staged x 76 / 28 us, bulk-copy ring 1: 73 / 16.7, 2: 69 / 16.4, 3: 63 / 17.8 us.
+template <int BS, int MODE>
+bool launch_split_tma(glims_ctx* c, const SellPattern& p, const float* A, const float* x, float* out, int s0, int ns,
+                      const float* rhs, const float* dinv, float* d, float c1, float c2) {
+    static const int cfg = [] { const char* e = std::getenv("GLIMS_SPLIT_TMA"); return e ? atoi(e) : 3; }();
+    if (!cfg || ns <= 0) return false;
+    if (cfg == 2) launch_split_tma_cfg<BS, MODE, 2, 4, 24>(c, p, A, x, out, s0, ns, rhs, dinv, d, c1, c2);
+    else if (cfg == 3) launch_split_tma_cfg<BS, MODE, 2, 3, 12>(c, p, A, x, out, s0, ns, rhs, dinv, d, c1, c2);
+    else launch_split_tma_cfg<BS, MODE, 4, 3, 24>(c, p, A, x, out, s0, ns, rhs, dinv, d, c1, c2);
+    return true;
 }
 
 // thread per aggregate: better for the large fine-level restriction (tens of thousands of aggregates)
@@ -829,6 +1068,10 @@ __global__ void k_dense_matvec32(const float* __restrict__ M, const float* __res
     if (lane == 0) y[row] = s;
 }
 
+inline bool split_staged() {      // GLIMS_SPLIT_STAGED=0|1: x blocks of the coarse-level products staged in shared memory
+    static const int v = [] { const char* e = std::getenv("GLIMS_SPLIT_STAGED"); return e ? atoi(e) : 1; }();
+    return v != 0;
+}
 inline int sgrid(i64 n) { i64 g = (n + TPB - 1) / TPB; return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g)); }
 
 void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) {
@@ -837,13 +1080,19 @@ void spmv32(glims_ctx* c, Level& l, const float* x, float* y, const float* rhs) 
         const int s0 = l.dist_rows ? l.row0 / 32 : 0, ns = l.dist_rows ? l.rows / 32 : p.n_slices;     // own rows only
         int g = ns < 148 * 16 ? ns : 148 * 16;
         if (g < 1) g = 1;
-#define SPLIT_GO(BS, RES, MT, AP, US) k_spmv32_split<BS, RES, MT><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, y, p.n_rows, s0, ns, rhs, US)
+#define SPLIT_GO(BS, RES, MT, AP, US) do { if (split_staged()) k_spmv32_split<BS, RES, MT, true><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, y, p.n_rows, s0, ns, rhs, US); \
+                                             else k_spmv32_split<BS, RES, MT, false><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, y, p.n_rows, s0, ns, rhs, US); } while (0)
         if (l.A16) {
             if (l.bs == 6) { if (rhs) SPLIT_GO(6, true, __half, l.A16, l.a16_unscale); else SPLIT_GO(6, false, __half, l.A16, l.a16_unscale); }
             else { if (rhs) SPLIT_GO(3, true, __half, l.A16, l.a16_unscale); else SPLIT_GO(3, false, __half, l.A16, l.a16_unscale); }
         } else {
-            if (l.bs == 6) { if (rhs) SPLIT_GO(6, true, float, l.A32, 1.f); else SPLIT_GO(6, false, float, l.A32, 1.f); }
-            else { if (rhs) SPLIT_GO(3, true, float, l.A32, 1.f); else SPLIT_GO(3, false, float, l.A32, 1.f); }
+            bool done;
+            if (l.bs == 6) done = rhs ? launch_split_tma<6, 1>(c, p, l.A32, x, y, s0, ns, rhs, nullptr, nullptr, 0.f, 0.f) : launch_split_tma<6, 0>(c, p, l.A32, x, y, s0, ns, nullptr, nullptr, nullptr, 0.f, 0.f);
+            else done = rhs ? launch_split_tma<3, 1>(c, p, l.A32, x, y, s0, ns, rhs, nullptr, nullptr, 0.f, 0.f) : launch_split_tma<3, 0>(c, p, l.A32, x, y, s0, ns, nullptr, nullptr, nullptr, 0.f, 0.f);
+            if (!done) {
+                if (l.bs == 6) { if (rhs) SPLIT_GO(6, true, float, l.A32, 1.f); else SPLIT_GO(6, false, float, l.A32, 1.f); }
+                else { if (rhs) SPLIT_GO(3, true, float, l.A32, 1.f); else SPLIT_GO(3, false, float, l.A32, 1.f); }
+            }
         }
 #undef SPLIT_GO
     } else {
@@ -877,9 +1126,14 @@ void cheb_step32(glims_ctx* c, Level& l, const float* b, const float* x, float* 
         const int s0 = l.dist_rows ? l.row0 / 32 : 0, ns = l.dist_rows ? l.rows / 32 : p.n_slices;     // own rows only
         int g = ns < 148 * 16 ? ns : 148 * 16;
         if (g < 1) g = 1;
-#define SPLITC_GO(BS, MT, AP, US) k_spmv32_split_cheb<BS, MT><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, xn, p.n_rows, s0, ns, b, l.dinv32, l.d32, c1, c2, US)
+#define SPLITC_GO(BS, MT, AP, US) do { if (split_staged()) k_spmv32_split_cheb<BS, MT, true><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, xn, p.n_rows, s0, ns, b, l.dinv32, l.d32, c1, c2, US); \
+                                        else k_spmv32_split_cheb<BS, MT, false><<<g, 32 * BS, 0, c->stream>>>(p.slice_off, p.slice_w, p.col, AP, x, xn, p.n_rows, s0, ns, b, l.dinv32, l.d32, c1, c2, US); } while (0)
         if (l.A16) { if (l.bs == 6) SPLITC_GO(6, __half, l.A16, l.a16_unscale); else SPLITC_GO(3, __half, l.A16, l.a16_unscale); }
-        else { if (l.bs == 6) SPLITC_GO(6, float, l.A32, 1.f); else SPLITC_GO(3, float, l.A32, 1.f); }
+        else {
+            const bool done = l.bs == 6 ? launch_split_tma<6, 2>(c, p, l.A32, x, xn, s0, ns, b, l.dinv32, l.d32, c1, c2)
+                                        : launch_split_tma<3, 2>(c, p, l.A32, x, xn, s0, ns, b, l.dinv32, l.d32, c1, c2);
+            if (!done) { if (l.bs == 6) SPLITC_GO(6, float, l.A32, 1.f); else SPLITC_GO(3, float, l.A32, 1.f); }
+        }
 #undef SPLITC_GO
     } else {
         // one 256-row tile per CTA: the hardware scheduler balances tiles of different widths, and the grid does not depend on
@@ -1125,6 +1379,11 @@ void amg_setup(glims_ctx* c) {
         if (level == 1 && dist) for (int i = 0; i < n; ++i) excl[i] = pad1[i];      // padding nodes of the rank segments
         std::vector<int> agg;
         int na = aggregate(g, n, excl, agg);
+        {
+            const char* es = std::getenv("GLIMS_AMG_SORT");
+            const int window = es ? atoi(es) : 0;      // measured at C4: 23 % fewer level-1 slots, but the smoother step got slower (75 -> 82 us: gather locality) and PCG needed 5 % more iterations -- off by default
+            if (window > 0) relabel_by_degree(g, n, agg, na, window);
+        }
         if (!(dist && level == 0) && (na == 0 || na >= n)) break;
         // centroids, offsets, member lists
         std::vector<double> Xc((i64)std::max(na, 1) * D, 0.0);
@@ -1371,6 +1630,15 @@ bool amg_time_coarse(glims_ctx* c) {
     float* cur = ((amg->coarse_degree - 1) & 1) ? amg->L[1].x32 : amg->L[1].y32;
     coarse_correction32(c, amg, 1, cur);
     if (std::getenv("GLIMS_VERBOSE")) { cudaStreamSynchronize(c->stream); amg_fused_print_phases(amg); }
+    return true;
+}
+
+// one fused smoother step on level 1 (glims_time_kernel 10)
+bool amg_time_level1_step(glims_ctx* c) {
+    Amg* amg = c->amg;
+    if (!amg || amg->L.size() < 3 || !amg->L[1].y32) return false;
+    Level& l = amg->L[1];
+    cheb_step32(c, l, l.b32, l.x32, l.y32, 0.3f, 0.5f);
     return true;
 }
 

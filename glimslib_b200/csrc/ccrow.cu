@@ -18,6 +18,7 @@
 // travel in the list: 8 bytes per (row, element) pair instead of 64 bytes per element of eslot + RED.ADD traffic).
 #include "common.h"
 #include "geom.cuh"
+#include "tma.cuh"
 #include <thrust/device_ptr.h>
 #include <thrust/device_vector.h>
 #include <thrust/sort.h>
@@ -291,30 +292,6 @@ k_cc_rows(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, co
 // the bulk-copy engine (cp.async.bulk ... mbarrier::complete_tx) and the warp gathers the slice's column values while the
 // copies fly; the pair loop then reads only shared memory.  No register staging, no long-scoreboard stall inside the loop,
 // and ~10 KB in flight per warp instead of what fits in registers.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
 template <int D, bool WK>
 __global__ void __launch_bounds__(CC_TPB)
 k_cc_rows_tma(const i64* __restrict__ slice_off, const int* __restrict__ slice_w, const int* __restrict__ col, int n_rows,

@@ -263,6 +263,7 @@ void amg_free(glims_ctx* c);
 void amg_vcycle(glims_ctx* c, const double* r, double* z, bool fp32);
 void amg_check(glims_ctx* c);              // throws if a device-side wait inside the V-cycle timed out
 bool amg_time_coarse(glims_ctx* c);        // false: hierarchy has fewer than three levels
+bool amg_time_level1_step(glims_ctx* c);   // false: hierarchy has fewer than three levels
 bool amg_time_fine_step(glims_ctx* c);     // false: no FP32 hierarchy yet   // z = M^-1 r on K_uu ([n_v][dim] vectors)
 
 // ---------------- comm.cu

@@ -1243,6 +1243,7 @@ int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t rep
             case 3: launch_spmv(c, 2, dx, dy); break;
             case 4: launch_assemble(c, GLIMS_ASM_RESIDUAL, variant); break;
             case 5: launch_assemble(c, GLIMS_ASM_RESIDUAL | GLIMS_ASM_KCC, variant); break;
+            case 10: if (!amg_time_level1_step(c)) throw GlError(GLIMS_ERR_STATE, "glims_time_kernel 10: no three-level FP32 hierarchy"); break;
             case 9: if (!amg_time_coarse(c)) throw GlError(GLIMS_ERR_STATE, "glims_time_kernel 9: no three-level FP32 hierarchy"); break;
             case 7: launch_cc_rows(c, true, true); break;
             case 8: launch_fu(c, false); break;

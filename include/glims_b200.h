@@ -175,7 +175,8 @@ int glims_spmv(glims_ctx* c, int32_t which, const double* x, double* y);
    pass of the block-triangular solver), 6 = one fused Chebyshev smoother step of the V-cycle's fine level (FP16 matrix,
    FP32 vectors; needs a step with GLIMS_PC_AMG first), 7 = the row-walk K_cc + F_c kernel alone (what glims_step launches
    per Newton iteration), 8 = F_u = K_uu u + K_uc c by SpMV alone, 9 = the coarse-grid correction below level 1 of the
-   V-cycle (levels >= 2: one persistent kernel, or its launch sequence with GLIMS_AMG_FUSED=0). flush_l2 != 0 writes a
+   V-cycle (levels >= 2: one persistent kernel, or its launch sequence with GLIMS_AMG_FUSED=0), 10 = one fused smoother step
+   on level 1 of the V-cycle. flush_l2 != 0 writes a
    >L2-sized buffer between launches (outside the timed events). */
 int glims_time_kernel(glims_ctx* c, int32_t kernel, int32_t variant, int32_t reps, int32_t flush_l2,
                       float* ms_avg);
