@@ -465,14 +465,14 @@ def main():
         kernels["_pattern"] = {"nnz_blocks": int(nnzb), "sell_slots": int(eng.nslots),
                                "sell_padding": float(eng.nslots) / float(nnzb) - 1.0}
         if "ms" in kernels.get("smoother_step_fp16", {}):
-            # dominant kernel of the step (profiles/r02_launch_summary.csv): 3 launches per PCG iteration
+            # dominant kernel of the step (profiles/r02b_launch_summary.csv): 3 launches per PCG iteration
             k = kernels["smoother_step_fp16"]
             roof = {"bound": "hbm", "kernel": "k_spmv32_row_cheb<3,__half> (fused Chebyshev smoother step, fine level of the V-cycle)",
                     "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": k["frac"],
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this kernel on this
                     # workload (profiles/r02_ncu_summary.md); only valid for the default mesh on one GPU
-                    "traffic": 786.4e6 if default_c4 else None,
-                    "traffic_source": "profiles/r02_ncu_summary.md (ncu --set full, dram read 756.2 MB + write 30.2 MB)",
+                    "traffic": 746.7e6 if default_c4 else None,
+                    "traffic_source": "profiles/r02_ncu_summary.md, second pass (ncu --set full, dram read 715.0 MB + write 31.8 MB)",
                     "peak_source": peak_src}
         else:
             k = kernels["spmv_kuu"]
