@@ -961,7 +961,10 @@ template <int BS, int MODE, int SL, int NST, int CH>
 void launch_split_tma_cfg(glims_ctx* c, const SellPattern& p, const float* A, const float* x, float* out, int s0, int ns,
                           const float* rhs, const float* dinv, float* d, float c1, float c2) {
     constexpr size_t smem = split_tma_smem<BS, SL, NST, CH>();
-    static int grid_cap = 0;
+    static int grid_caps[64] = {0};          // per device: the shared-memory attribute is a per-device property of the function
+    int dev = 0;
+    GL_CUDA(cudaGetDevice(&dev));
+    int& grid_cap = grid_caps[dev & 63];
     if (!grid_cap) {
         GL_CUDA(cudaFuncSetAttribute(k_split_tma<BS, MODE, SL, NST, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         grid_cap = resident_grid((const void*)k_split_tma<BS, MODE, SL, NST, CH>, 32 * BS, smem);
