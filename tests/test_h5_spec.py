@@ -104,3 +104,26 @@ def test_the_verifier_rejects_broken_files(tmp_path):
     oh = struct.unpack_from("<Q", b, 64)[0]
     with pytest.raises(h5spec.SpecError):                                  # message count of the root object header
         h5spec.verify(_corrupt(b, oh + 2, struct.pack("<H", struct.unpack_from("<H", b, oh + 2)[0] + 1)))
+
+
+def test_mesh_and_label_files(tmp_path):
+    """N3: data_io.save_mesh_hdf5 / save_functions_hdf5 (reference data_io.py:663-713, 751-760) through the same verifier."""
+    from glimslib_b200.utils import data_io as dio
+    mesh = fenics.UnitSquareMesh(4, 3)
+    labels = fenics.MeshFunction("size_t", mesh, 2)
+    labels.array()[:] = np.arange(mesh.num_cells()) % 3
+    p = str(tmp_path / "mesh.h5")
+    dio.save_mesh_hdf5(mesh, p, subdomains=labels)
+    data, groups = h5spec.verify(open(p, "rb").read())
+    topo = [k for k in data if k.startswith("/mesh/") and data[k][0].ndim == 2 and data[k][0].dtype.kind in "iu"]
+    geom = [k for k in data if k.startswith("/mesh/") and data[k][0].dtype.kind == "f"]
+    assert topo and geom
+    assert np.array_equal(np.sort(data[topo[0]][0], axis=1), np.sort(mesh.cells, axis=1))
+    assert np.allclose(data[geom[0]][0], mesh.coords)
+    vals = [v for k, (v, _) in data.items() if k.startswith("/subdomains/") and v.size == mesh.num_cells() and v.ndim == 1]
+    assert any(np.array_equal(np.asarray(v, dtype=np.int64), labels.array()) for v in vals)
+    V = fenics.FunctionSpace(mesh, "CG", 1)
+    f = fenics.project(fenics.Expression("x[0]+2*x[1]", degree=1), V)
+    dio.save_functions_hdf5({"f": f}, str(tmp_path / "f.h5"), time_step=0)
+    data, _ = h5spec.verify(open(str(tmp_path / "f.h5"), "rb").read())
+    assert np.array_equal(data["/f/vector_0"][0], f.vector().get_local())
