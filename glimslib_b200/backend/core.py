@@ -192,20 +192,73 @@ class SubDomain:
         meshfunction.array()[ok] = value
 
 
+class _Coefficient:
+    """Scalar coefficients multiply into integrands: ``Constant(2.0) * c * ds(3)`` (the boundary terms of the reference,
+    helper_classes.py:896-908, and its unit tests build such expressions and hand them to ``assemble``)."""
+    __array_priority__ = 1000          # numpy scalars defer to these operators
+
+    def __mul__(self, other): return Integrand([self]) * other
+    def __rmul__(self, other): return Integrand(_factors(other) + [self])
+
+
+def _factors(obj):
+    if isinstance(obj, Integrand):
+        return list(obj.factors)
+    if isinstance(obj, (int, float, np.integer, np.floating)):
+        return [Constant(float(obj))]
+    if isinstance(obj, (_Coefficient, ComponentView)):
+        return [obj]
+    raise TypeError("cannot multiply an integrand by %r" % type(obj).__name__)
+
+
+class Integrand:
+    """Product of scalar coefficients, each affine per cell (Constant, P1 function or sub-function, degree-1 expression)."""
+
+    def __init__(self, factors): self.factors = list(factors)
+
+    def __mul__(self, other):
+        if isinstance(other, Measure):
+            return Form([(self, other)])
+        return Integrand(self.factors + _factors(other))
+
+    def __rmul__(self, other): return Integrand(_factors(other) + self.factors)
+
+
+class Form:
+    """Sum of integrand x measure terms; ``assemble(form)`` integrates it exactly (scalar functionals only -- the residual
+    and Jacobian of the hot path are not built from forms, they are the kernels of DESIGN.md section 5)."""
+
+    def __init__(self, terms): self.terms = list(terms)
+
+    def __add__(self, other):
+        if isinstance(other, (int, float)) and other == 0:
+            return self
+        return Form(self.terms + other.terms)
+
+    __radd__ = __add__
+
+    def __neg__(self): return Form([(Integrand([Constant(-1.0)] + i.factors), m) for i, m in self.terms])
+    def __sub__(self, other): return self + (-other)
+
+
 class Measure:
     def __init__(self, kind, subdomain_data=None, subdomain_id=None):
-        self.kind, self.subdomain_data, self.subdomain_id = kind, subdomain_data, subdomain_id
+        self.kind, self._data, self.subdomain_id = kind, subdomain_data, subdomain_id
+
+    def subdomain_data(self): return self._data
 
     def __call__(self, subdomain_id=None, subdomain_data=None):
-        return Measure(self.kind, subdomain_data if subdomain_data is not None else self.subdomain_data,
+        return Measure(self.kind, subdomain_data if subdomain_data is not None else self._data,
                        subdomain_id if subdomain_id is not None else self.subdomain_id)
+
+    def __rmul__(self, other): return Integrand(_factors(other)) * self
 
 
 dx, ds, dS = Measure("dx"), Measure("ds"), Measure("dS")
 
 
 # ------------------------------------------------------------------------------------------------ coefficients
-class Constant:
+class Constant(_Coefficient):
     def __init__(self, value, **kw):
         self._v = np.atleast_1d(np.asarray(value, dtype=np.float64)).ravel()
         self._scalar = np.ndim(value) == 0
@@ -218,7 +271,7 @@ class Constant:
     def ufl_shape(self): return () if self._scalar else (len(self._v),)
 
 
-class Expression:
+class Expression(_Coefficient):
     """``fenics.Expression(cpp_code | (cpp, ...), degree=..., **params)`` or a Python subclass overriding
     ``eval(values, x)`` (and optionally ``value_shape``)."""
 
@@ -425,9 +478,11 @@ class ComponentView:
 
     def geometric_dimension(self): return self.function.geometric_dimension()
     def __len__(self): return self.c1 - self.c0
+    def __mul__(self, other): return Integrand([self]) * other
+    def __rmul__(self, other): return Integrand(_factors(other) + [self])
 
 
-class Function:
+class Function(_Coefficient):
     def __init__(self, V, name=None, **kw):
         if isinstance(V, Function):
             self._V, self._x = V._V, V._x.copy()
@@ -549,6 +604,91 @@ def _values_on(V, src):
     return v
 
 
+# ------------------------------------------------------------------------------------------------ scalar functionals
+def _scalar_vertex_values(f, mesh):
+    """Values at the mesh vertices of a scalar coefficient that is affine per cell."""
+    nv = mesh.num_vertices()
+    if isinstance(f, Constant):
+        if f.value_size() != 1:
+            raise TypeError("assemble: only scalar integrands are supported (use inner/dot on the host side)")
+        return np.full(nv, float(f))
+    if isinstance(f, Function):
+        V = f.function_space()
+        if V.ncomp != 1 or V._element.family != "CG":
+            raise TypeError("assemble: factors must be scalar P1 functions")
+        return f.node_values()[:, 0]
+    if isinstance(f, ComponentView):
+        v = f.values()
+        if v.shape[1] != 1:
+            raise TypeError("assemble: factors must be scalar sub-functions")
+        return v[:, 0]
+    if isinstance(f, Expression):
+        v = np.asarray(f.eval_points(mesh.coords)).reshape(nv, -1)
+        if v.shape[1] != 1:
+            raise TypeError("assemble: factors must be scalar expressions")
+        return v[:, 0]
+    raise TypeError("assemble: unsupported factor %r" % type(f).__name__)
+
+
+def _integrate(integrand, measure):
+    """Exact integral of a product of per-cell affine scalars over the cells (dx) or exterior facets (ds) the measure
+    selects: the product is expanded in barycentric monomials and int lambda^alpha = |e| k! alpha! / (k + |alpha|)!."""
+    from math import factorial
+    data = measure.subdomain_data()
+    mesh = data.mesh() if data is not None else None
+    for f in integrand.factors:
+        if mesh is not None:
+            break
+        if isinstance(f, Function):
+            mesh = f.function_space().mesh()
+        elif isinstance(f, ComponentView):
+            mesh = f.function.function_space().mesh()
+    if mesh is None:
+        raise ValueError("assemble: the form does not name a mesh (no subdomain data, no function)")
+    if measure.kind == "dx":
+        ent = np.asarray(mesh.cells)
+        sel = np.ones(len(ent), dtype=bool)
+        if measure.subdomain_id is not None:
+            sel = np.asarray(data.array()) == measure.subdomain_id
+    elif measure.kind == "ds":
+        ids, ent, _ = mesh.exterior_facets()
+        sel = np.ones(len(ent), dtype=bool)
+        if measure.subdomain_id is not None:
+            sel = np.asarray(data.array())[ids] == measure.subdomain_id
+    else:
+        raise NotImplementedError("assemble: interior-facet measures are not part of the drop-in")
+    ent = ent[sel]
+    if len(ent) == 0:
+        return 0.0
+    X = np.asarray(mesh.coords)[ent]                                    # (n, k+1, dim)
+    k = ent.shape[1] - 1
+    E = X[:, 1:, :] - X[:, :1, :]
+    vol = np.sqrt(np.abs(np.linalg.det(E @ E.transpose(0, 2, 1)))) / factorial(k) if k > 0 else np.ones(len(ent))
+    poly = {(0,) * (k + 1): np.ones(len(ent))}
+    for f in integrand.factors:
+        V = _scalar_vertex_values(f, mesh)[ent]                         # (n, k+1)
+        nxt = {}
+        for alpha, coef in poly.items():
+            for a in range(k + 1):
+                b = alpha[:a] + (alpha[a] + 1,) + alpha[a + 1:]
+                nxt[b] = nxt.get(b, 0.0) + coef * V[:, a]
+        poly = nxt
+    total = 0.0
+    for alpha, coef in poly.items():
+        w = factorial(k) * np.prod([factorial(a) for a in alpha]) / factorial(k + sum(alpha))
+        total += w * float(np.dot(coef, vol))
+    return total
+
+
+def assemble(form):
+    """``fenics.assemble`` for scalar functionals (sums of coefficient products times dx / ds measures)."""
+    if isinstance(form, (int, float)):
+        return float(form)
+    if not isinstance(form, Form):
+        raise TypeError("assemble: expected a Form (integrand * measure), got %r" % type(form).__name__)
+    return float(sum(_integrate(i, m) for i, m in form.terms))
+
+
 def project(v, V=None, **kw):
     if V is None:
         raise ValueError("project(v, V): V is required")
@@ -663,6 +803,5 @@ def _no_ufl(name):
     return f
 
 
-inner, grad, sym, tr, det, dot, div, sqrt, derivative, Identity, assemble, solve = (
-    _no_ufl(n) for n in ("inner", "grad", "sym", "tr", "det", "dot", "div", "sqrt", "derivative", "Identity",
-                         "assemble", "solve"))
+inner, grad, sym, tr, det, dot, div, sqrt, derivative, Identity, solve = (
+    _no_ufl(n) for n in ("inner", "grad", "sym", "tr", "det", "dot", "div", "sqrt", "derivative", "Identity", "solve"))

@@ -12,6 +12,13 @@ from glimslib_b200.backend.problem import (NonlinearVariationalProblem, Nonlinea
                                             CoupledRDMechanicsForm, SolverNotConverged)
 from glimslib_b200 import config
 
+import types as _types
+
+# dolfin's module paths of the Function class (2018+: dolfin.function.function.Function, before: dolfin.functions.Function);
+# the reference's unit tests compare types against them (simulation_helpers/test_unit_subSpaces.py:116-129)
+function = _types.SimpleNamespace(function=_types.SimpleNamespace(Function=Function))      # noqa: F405
+functions = _types.SimpleNamespace(Function=Function)                                      # noqa: F405
+
 if config.USE_ADJOINT:
     raise ImportError("USE_ADJOINT: the dolfin-adjoint tape is not part of the B200 hot path")
 

@@ -53,6 +53,9 @@ class DiscontinuousScalar:
 class SubSpaces:
     """Book-keeping for functions living on several sub-spaces (helper_classes.py:66-232)."""
 
+    _ATTR = {"elements": "_elements", "ivs": "_inital_value_expressions", "functionspaces": "_functionspaces",
+             "bcs_dirichlet": "_bcs_dirichlet", "bcs_von_neumann": "_bcs_von_neumann"}
+
     def __init__(self, names=None):
         self.logger = logging.getLogger(__name__)
         self.names = dict(names or {})
@@ -82,6 +85,7 @@ class SubSpaces:
             self.logger.warning("Attribute '%s' already exists ... do nothing." % name)
             return
         self._store[name] = d
+        setattr(self, self._ATTR[name], d)      # the reference keeps each table as a private attribute of this name
 
     def _get(self, name, subspace_id=None, subspace_name=None):
         if subspace_id is None and subspace_name is None:
@@ -407,13 +411,25 @@ class BoundaryConditions:
             m = spec["measure"]
             mesh = self._functionspace._mesh
             ext = mesh.facets()[2][:, 1] < 0
-            fids = np.nonzero(ext & (np.asarray(m.subdomain_data.array()) == m.subdomain_id))[0]
+            fids = np.nonzero(ext & (np.asarray(m.subdomain_data().array()) == m.subdomain_id))[0]
             out.append((fids, subspace_id, spec["bc_value"]))
         return out
 
     def implement_von_neumann_bc(self, product_component, subspace_id=None):
-        """Kept for API compatibility: returns the facet terms the backend integrates into the load vector."""
-        return self.neumann_terms(subspace_id)
+        """``sum_i g_N,i * product_component * ds(boundary_i)`` over the von Neumann conditions of the sub-space
+        (helper_classes.py:861-908).  With a coefficient product (``param * c``) this is a scalar form for
+        ``fenics.assemble``; with a test function it names the facet terms the backend integrates into the load vector
+        (`neumann_terms`, what `_setup_problem` uses)."""
+        if isinstance(product_component, tuple) and product_component and product_component[0] == "test":
+            return self.neumann_terms(subspace_id)
+        has_sub = self._functionspace.has_subspaces
+        if has_sub != (subspace_id is not None):
+            self.logger.error("Choice of subspace ID not compatible with functionspace")
+            return 0.0
+        terms = [spec["bc_value"] * product_component * spec["measure"]
+                 for spec in getattr(self, "von_neumann_bcs", {}).values()
+                 if not has_sub or spec.get("subspace_id") == subspace_id]
+        return sum(terms) if terms else 0.0
 
 
 # ==================================================================================================

@@ -226,3 +226,35 @@ def test_mesh_hdf5_round_trip(tmp_path):
     dio.save_functions_hdf5({"f": f}, str(tmp_path / "f.h5"), time_step=0)
     g = dio.read_function_hdf5("f", V, str(tmp_path / "f.h5"))
     assert np.array_equal(g.vector().get_local(), f.vector().get_local())
+
+
+def test_assemble_scalar_functionals_exactly():
+    """fenics.assemble of coefficient products over dx / ds measures (what BoundaryConditions.implement_von_neumann_bc
+    returns for a coefficient, helper_classes.py:861-908): products of up to three per-cell affine factors are exact."""
+    mesh = fenics.UnitSquareMesh(6, 5)
+    V = fenics.FunctionSpace(mesh, "CG", 1)
+    x = fenics.project(fenics.Expression("x[0]", degree=1), V)
+    y = fenics.project(fenics.Expression("x[1]", degree=1), V)
+    one = fenics.Constant(1.0)
+    assert abs(fenics.assemble(x * y * fenics.dx) - 0.25) < 1e-14
+    assert abs(fenics.assemble(2.0 * x * x * y * fenics.dx) - 2.0 / 6.0) < 1e-14
+    # exterior facets: the whole boundary, then the top edge only through a facet MeshFunction
+    assert abs(fenics.assemble(one * x * fenics.ds) - 2.0) < 1e-14           # int x over the four edges: 0.5 + 0.5 + 1 + 0
+
+    class Top(fenics.SubDomain):
+        def inside(self, p, on_boundary):
+            return on_boundary and p[1] > 1.0 - 1e-12
+    mf = fenics.MeshFunction("size_t", mesh, 1)
+    mf.set_all(0)
+    Top().mark(mf, 7)
+    ds = fenics.ds(subdomain_data=mf)
+    assert ds.subdomain_data() is mf
+    assert abs(fenics.assemble(x * y * ds(7)) - 0.5) < 1e-14
+    assert abs(fenics.assemble(x * ds(7) + fenics.Constant(3.0) * y * ds(7)) - 3.5) < 1e-14
+    # cells by label
+    lab = fenics.MeshFunction("size_t", mesh, 2)
+    lab.array()[:] = (mesh.cell_midpoints()[:, 0] > 0.5).astype(int)
+    dx = fenics.dx(subdomain_data=lab)
+    assert abs(fenics.assemble(one * one * dx(1)) - 0.5) < 1e-14
+    with pytest.raises(TypeError):
+        fenics.assemble(fenics.Constant((1.0, 2.0)) * x * fenics.dx)
