@@ -900,5 +900,28 @@ class PostProcessTumorGrowth:
     def plot_all(self, *a, **k):
         self.logger.warning("plotting is not part of the B200 hot path -- skipping plots")
 
+    def save_all(self, save_method="xdmf", clear_all=False, selection=slice(None), output_dir=None):
+        """Re-writes recorded (e.g. reloaded) solutions through the Results writers, per-step merged VTUs for the VTK
+        method (helper_classes.py:1922-1941)."""
+        from glimslib_b200.utils import data_io as dio
+        if output_dir is not None:
+            self.set_output_dir(output_dir)
+        res = self._results
+        res.set_save_output_dir(self.get_output_dir())
+        res.save_solution_start(method=save_method, clear_all=clear_all)
+        if isinstance(selection, slice):
+            steps = res.get_recording_steps()[selection]
+        elif isinstance(selection, list):
+            steps = selection
+        else:
+            self.logger.error("cannot handle selection '%s'" % (selection,))
+            steps = []
+        for step in steps:
+            t = res.get_result(recording_step=step).get_time_step()
+            res.save_solution(step, t, function=res.get_solution_function(recording_step=step), method=save_method)
+            if save_method != "xdmf":
+                dio.merge_vtus_timestep(self.get_output_dir(), step, remove=False, reference_file_path=None)
+        res.save_solution_end(method=save_method)
+
 
 PostProcessTumorGrowthBrain = PostProcessTumorGrowth
