@@ -514,6 +514,17 @@ class Function(_Coefficient):
 
     def interpolate(self, expr): self.assign(expr)
 
+    def _combine(self, other, sign):
+        if not isinstance(other, Function) or other._x.shape != self._x.shape:
+            raise TypeError("only functions of the same space can be added / subtracted")
+        out = self.copy(deepcopy=True)
+        out._x[:] = self._x + sign * other._x
+        out._touch()
+        return out
+
+    def __sub__(self, other): return self._combine(other, -1.0)      # a Function (the reference gets a UFL sum it then stores)
+    def __add__(self, other): return self._combine(other, 1.0)
+
     def sub(self, i, deepcopy=False):
         S = self._V.sub(i)
         if deepcopy:

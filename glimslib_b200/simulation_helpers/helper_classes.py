@@ -925,3 +925,61 @@ class PostProcessTumorGrowth:
 
 
 PostProcessTumorGrowthBrain = PostProcessTumorGrowth
+
+
+class AnyDimPoint(fenics.Point):
+    """``Point`` from a tuple of 1 - 3 coordinates or a single float (helper_classes.py:23-45)."""
+
+    def __init__(self, coordinates):
+        if isinstance(coordinates, (int, float)):
+            coordinates = (coordinates,)
+        fenics.Point.__init__(self, *coordinates)
+
+
+class Comparison:
+    """Inter-run metric of two simulations that share a function space (helper_classes.py:1975-2035; the reference compares
+    TumorGrowth against TumorGrowthBrain with it, test_case_comparison_2D_atlas.py:203-210): difference fields and L2 error
+    norms per shared recording step, over the mixed space and per sub-space."""
+
+    def __init__(self, sim1, sim2):
+        self.sim1, self.sim2 = sim1, sim2
+        self.difference = Results(sim1.functionspace)
+        s2 = set(sim2.results.get_recording_steps())
+        self.shared_recording_steps = [k for k in sim1.results.get_recording_steps() if k in s2]
+
+    def _pair(self, recording_step, subspace_name=None):
+        return (self.sim1.results.get_solution_function(subspace_name=subspace_name, recording_step=recording_step),
+                self.sim2.results.get_solution_function(subspace_name=subspace_name, recording_step=recording_step))
+
+    def compute_difference(self, recording_step):
+        obs = self.sim1.results.get_result(recording_step=recording_step)
+        u1, u2 = self._pair(recording_step)
+        self.difference.add_to_results(current_sim_time=obs.get_time(), current_time_step=obs.get_time_step(),
+                                       recording_step=recording_step, field=u1 - u2, replace=True)
+
+    def compute_errornorm(self, recording_step):
+        return fenics.errornorm(*self._pair(recording_step))
+
+    def compute_errornorm_by_subspace(self, recording_step):
+        return {name: fenics.errornorm(*self._pair(recording_step, name))
+                for name in self.difference._functionspace.subspaces.get_subspace_names()}
+
+    def get_difference_by_subspace(self, recording_step):
+        if not self.difference.exists_recording_step(recording_step):
+            self.compute_difference(recording_step)
+        return {name: self.difference.get_solution_function(subspace_name=name, recording_step=recording_step)
+                for name in self.difference._functionspace.subspaces.get_subspace_names()}
+
+    def compute_max_difference(self, recording_step):
+        if not self.difference.exists_recording_step(recording_step):
+            self.compute_difference(recording_step)
+        return float(np.max(self.difference.get_solution_function(recording_step=recording_step).vector().get_local()))
+
+    def compare(self, selection=slice(None)):
+        import pandas as pd
+        rows = []
+        for step in self.shared_recording_steps[selection]:
+            row = {"recording_step": step, "errornorm": self.compute_errornorm(step)}
+            row.update({"errornorm_" + k: v for k, v in self.compute_errornorm_by_subspace(step).items()})
+            rows.append(row)
+        return pd.DataFrame(rows)
