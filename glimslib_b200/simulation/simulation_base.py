@@ -10,6 +10,8 @@ record every ``keep_nth`` steps, ``u_previous.assign(solution)``, then ``solutio
 """
 import logging
 import os
+
+import numpy as np
 from abc import ABC, abstractmethod
 
 from glimslib_b200 import fenics_local as fenics
@@ -123,6 +125,13 @@ class FenicsSimulation(ABC):
         self.results.save_solution_end(method=save_method)
         self.results.save_solution_hdf5()
         return self.solution
+
+    def _update_mesh_displacements(self, displacement):
+        """Adds a nodal displacement to the mesh coordinates (``fenics.ALE.move``, simulation_base.py:228-234; repeated calls
+        accumulate).  Host mesh only -- output in the deformed configuration; the device engine keeps the configuration it
+        was built on, exactly as the reference's solver does between calls."""
+        u = displacement.node_values() if hasattr(displacement, "node_values") else displacement.values()
+        self.mesh.coords += np.asarray(u).reshape(self.mesh.coords.shape)
 
     def reload_from_hdf5(self, path_to_hdf5, output_dir=config.output_dir_simulation_tmp):
         self.logger.info("-- Reloading from hdf5: ")

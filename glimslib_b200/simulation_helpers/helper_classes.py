@@ -48,6 +48,10 @@ class DiscontinuousScalar:
     def value_for_label(self, label):
         return float(self.value_by_label.get(label, 0.0))
 
+    def eval_cell(self, values, x, cell):
+        """DOLFIN's per-cell callback (helper_classes.py:55-58): the value of the cell's subdomain."""
+        values[0] = self.value_for_label(int(self.cell_function[cell.index() if callable(cell.index) else cell.index]))
+
 
 # ==================================================================================================
 class SubSpaces:
@@ -774,6 +778,11 @@ class Plotting:
             self.logger.warning("plotting is not part of the B200 hot path -- skipping plots")
             self._warned = True
 
+    def set_plot_output_dir(self, output_dir): self.plot_output_dir = output_dir
+    def plot(self, *a, **kw): self.plot_all(None)
+    def plot_concentration(self, *a, **kw): self.plot_all(None)
+    def plot_displacement(self, *a, **kw): self.plot_all(None)
+
 
 class PostProcessTumorGrowth:
     """Derived fields of recorded solutions (reference: helper_classes.py:1560-1618,1736-1786).
@@ -897,8 +906,28 @@ class PostProcessTumorGrowth:
         nrm = self._project(lambda cells, lam, sl: np.sqrt((np.einsum("qa,eai->eqi", lam, u[cells]) ** 2).sum(axis=2)))[:, 0]
         return self._as_function(nrm, "displacement_norm", False)
 
+    def get_concentration_deformed_configuration(self, recording_step=None):
+        """project(c * det(I + c gamma I) / det(I + grad u)) of the raw solution (helper_classes.py:1779-1786,
+        math_linear_elasticity.py:67-71): the deformation Jacobian is constant per cell (from the device's cell fields), the
+        rest a polynomial in the P1 concentration; host load vector, consistent-mass solve on the device."""
+        c = self.get_solution_concentration(recording_step=recording_step).vector().get_local()
+        gam = self._cell_coupling()
+        jt = np.asarray(self._fields(recording_step, cellwise=True)["total_jacobian"]).reshape(-1)
+        d = self._mesh.dim
+
+        def integrand(cells, lam, sl):
+            cq = np.einsum("qa,ea->eq", lam, c[cells])
+            return cq * (1.0 + gam[sl][:, None] * cq) ** d / jt[sl][:, None]
+        return self._as_function(self._project(integrand)[:, 0], "concentration_deformed_config", False)
+
     def plot_all(self, *a, **k):
         self.logger.warning("plotting is not part of the B200 hot path -- skipping plots")
+
+    def __getattr__(self, name):
+        # plot_concentration, plot_pressure, plot_for_pub, ...: tolerated like plot_all (plotting is out of scope)
+        if name.startswith("plot_"):
+            return lambda *a, **k: self.logger.warning("plotting is not part of the B200 hot path -- skipping %s" % name)
+        raise AttributeError("%s object has no attribute %r" % (type(self).__name__, name))
 
     def save_all(self, save_method="xdmf", clear_all=False, selection=slice(None), output_dir=None):
         """Re-writes recorded (e.g. reloaded) solutions through the Results writers, per-step merged VTUs for the VTK

@@ -105,5 +105,9 @@ def derived_fields(coords, cells, cell_mat, table, x):
     out["mech_expansion"] = mech
     out["growth_jacobian"] = project(coords, cells, lambda lam: (1.0 + np.einsum("qa,ea->eq", lam, mech[cells])) ** d)[:, 0]   # mle:29-30
     out["logistic_growth"] = project(coords, cells, lambda lam: rho[:, None] * cq(lam) * (1.0 - cq(lam)))[:, 0]   # mrd:2-3
+    # concentration in the deformed configuration, from the raw solution (helper_classes.py:1779-1786; mle:67-71):
+    # c * det(I + c gamma I) / det(I + grad u)
+    jt = np.linalg.det(I + gu)
+    out["concentration_deformed"] = project(coords, cells, lambda lam: cq(lam) * (1.0 + gam[:, None] * cq(lam)) ** d / jt[:, None])[:, 0]
     out["displacement_norm"] = project(coords, cells, lambda lam: np.sqrt((np.einsum("qa,eai->eqi", lam, u[cells]) ** 2).sum(axis=2)))[:, 0]
     return out

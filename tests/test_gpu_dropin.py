@@ -153,6 +153,7 @@ def test_postprocess_fields_match_numpy(tmp_path):
     assert rel(pp.get_growth_induced_jacobian(10).vector().get_local(), ref["growth_jacobian"]) < 1e-8
     assert rel(pp.get_logistic_growth(10).vector().get_local(), ref["logistic_growth"]) < 1e-9
     assert rel(pp.get_displacement_norm(10).vector().get_local(), ref["displacement_norm"]) < 1e-8
+    assert rel(pp.get_concentration_deformed_configuration(10).vector().get_local(), ref["concentration_deformed"]) < 1e-8
 
 
 @pytest.mark.parametrize("d", [2, 3])
