@@ -184,3 +184,63 @@ def read_function_hdf5(name, functionspace, path_to_file):
         hdf.read(f, name + "/vector_0")
         hdf.close()
         return f
+
+
+# ---- small dof / file helpers of the reference that need no image library (data_io.py:132-143, 277-308, 763-800) -------------
+def get_value_dimension_from_function(fenics_function):
+    """Number of value components (1 for a scalar element, dim for a vector element)."""
+    return int(fenics_function.function_space().ncomp)
+
+
+def get_dof_coordinate_map(functionspace):
+    """[n_dofs, gdim] coordinates, one row per dof."""
+    return np.asarray(functionspace.tabulate_dof_coordinates()).reshape(-1, functionspace.mesh().geometry().dim())
+
+
+def get_dofs_by_subspace(functionspace):
+    return {i: functionspace.sub(i).dofmap().dofs() for i in range(functionspace.num_sub_spaces())}
+
+
+def get_dofs_from_coord(dof_coord_map, coord, eps=1e-5):
+    """Indices of the dofs within ``eps`` of ``coord`` in every direction (None, with a message, if there is none)."""
+    coord = np.asarray(coord, dtype=float)[:dof_coord_map.shape[1]]
+    hit = np.nonzero(np.all(np.abs(dof_coord_map - coord[None, :]) < eps, axis=1))[0]
+    if len(hit) > 0:
+        return hit
+    print("Did not find vertex close to (%s) in mesh" % ", ".join(map(str, coord)))
+    return None
+
+
+def save_function_mesh(function, path_to_hdf5_function, labelfunction=None, subdomains=None):
+    """``<name>.h5`` (the function, as ``/function``) next to ``<name>_mesh.h5`` (mesh + cell labels)."""
+    if not path_to_hdf5_function.endswith(".h5"):
+        print("Provide path to '.h5' file")
+        return
+    path_to_hdf5_mesh = path_to_hdf5_function[:-3] + "_mesh.h5"
+    mesh = function.function_space().mesh()
+    fu.ensure_dir_exists(path_to_hdf5_mesh)
+    if labelfunction is not None:
+        from glimslib_b200.simulation_helpers.helper_classes import SubDomains
+        sd = SubDomains(mesh)
+        sd.setup_subdomains(label_function=labelfunction)
+        subdomains = sd.subdomains
+    save_mesh_hdf5(mesh, path_to_hdf5_mesh, subdomains=subdomains)
+    save_functions_hdf5({"function": function}, path_to_hdf5_function, time_step=None)
+
+
+def load_function_mesh(path_to_hdf5_function, functionspace="function", degree=1):
+    """Inverse of `save_function_mesh`: returns (function, mesh, subdomains, boundaries)."""
+    if not path_to_hdf5_function.endswith(".h5"):
+        print("Provide path to '.h5' file")
+        return None
+    path_to_hdf5_mesh = path_to_hdf5_function[:-3] + "_mesh.h5"
+    if not os.path.exists(path_to_hdf5_mesh):
+        print("Could not find mesh file: '%s'" % path_to_hdf5_mesh)
+        return None
+    mesh, subdomains, boundaries = read_mesh_hdf5(path_to_hdf5_mesh)
+    if functionspace == "function":
+        functionspace = fenics.FunctionSpace(mesh, "Lagrange", degree)
+    elif functionspace == "vector":
+        functionspace = fenics.VectorFunctionSpace(mesh, "Lagrange", degree)
+    function = read_function_hdf5("function", functionspace, path_to_hdf5_function)
+    return function, mesh, subdomains, boundaries

@@ -258,3 +258,31 @@ def test_assemble_scalar_functionals_exactly():
     assert abs(fenics.assemble(one * one * dx(1)) - 0.5) < 1e-14
     with pytest.raises(TypeError):
         fenics.assemble(fenics.Constant((1.0, 2.0)) * x * fenics.dx)
+
+
+def test_small_data_io_helpers(tmp_path):
+    """data_io.py:132-143, 277-308, 763-800 and file_utils.py:5-21: dof maps, coordinate lookup, function + mesh files."""
+    from glimslib_b200.utils import data_io as dio, file_utils as fu
+    assert fu.get_file_extension("/a/b.c/file.vtu") == "vtu" and fu.get_file_extension("/a/b.c/dir") is None
+    assert fu.ensure_dir_exists(str(tmp_path / "x" / "y.h5")) == str(tmp_path / "x") and (tmp_path / "x").is_dir()
+    mesh, labels = _labelled_mesh(4, 3)
+    el = fenics.MixedElement([fenics.VectorElement("Lagrange", mesh.ufl_cell(), 1), fenics.FiniteElement("Lagrange", mesh.ufl_cell(), 1)])
+    W = fenics.FunctionSpace(mesh, el)
+    by = dio.get_dofs_by_subspace(W)
+    assert sorted(by) == [0, 1] and len(by[0]) == 2 * mesh.num_vertices() and len(by[1]) == mesh.num_vertices()
+    assert sorted(np.concatenate([by[0], by[1]]).tolist()) == list(range(W.dim()))
+    xy = dio.get_dof_coordinate_map(W)
+    assert xy.shape == (W.dim(), 2)
+    hit = dio.get_dofs_from_coord(xy, (5.0, 5.0))
+    assert len(hit) == 3 and np.allclose(xy[hit], [5.0, 5.0])                 # u_x, u_y, c at the corner vertex
+    assert dio.get_dofs_from_coord(xy, (0.123, 0.456)) is None
+    V = fenics.FunctionSpace(mesh, "Lagrange", 1)
+    f = fenics.project(fenics.Expression("x[0]*x[1]+1", degree=1), V)
+    assert dio.get_value_dimension_from_function(f) == 1
+    U = fenics.VectorFunctionSpace(mesh, "Lagrange", 1)
+    assert dio.get_value_dimension_from_function(fenics.project(fenics.Constant((1.0, 2.0)), U)) == 2
+    p = str(tmp_path / "out" / "conc.h5")
+    dio.save_function_mesh(f, p, labelfunction=labels)
+    g, m2, sd2, _ = dio.load_function_mesh(p)
+    assert np.array_equal(m2.cells, mesh.cells) and np.array_equal(g.vector().get_local(), f.vector().get_local())
+    assert set(np.unique(sd2.array())) == {1, 2}
