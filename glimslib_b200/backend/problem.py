@@ -200,8 +200,9 @@ class NonlinearVariationalSolver:
         keep = len(dofs) - 1 - last
         return dofs[keep], vals[keep]
 
-    def solve(self):
-        """One Newton-Krylov solve on the device; returns (iterations, converged) like DOLFIN."""
+    def _prepare(self):
+        """Engine (created and configured on first use), current coefficients, Dirichlet data, solver options, and the
+        host -> device copies of whatever changed on the host since the last call.  Returns (engine, options, nl-params)."""
         from .. import _native as N
         form, prm = self.problem.form, self.parameters
         if self._engine is None:
@@ -232,6 +233,26 @@ class NonlinearVariationalSolver:
             eng.set_prev(up._x)
         if self._pushed_version[0] != (id(u), u.version):
             eng.set_state(u._x)
+        return eng, opts, nl
+
+    def adjoint_gradient(self, n_steps, levels, level_targets, u_target=None):
+        """``n_steps`` forward steps from (u_previous, u) and the discrete adjoint of the reference's image misfit of the final
+        state (image_based_optimization.py:660-700) on the device (``glims_adjoint``).  Returns ``(J, grad)`` with
+        ``grad[m] = (dJ/dD, dJ/drho, dJ/dgamma)`` of material row ``m`` of the form's table; ``u`` holds the final state."""
+        eng, opts, _ = self._prepare()
+        J, grad = eng.adjoint_gradient(int(n_steps), list(levels), np.asarray(level_targets, dtype=np.float64),
+                                       None if u_target is None else np.asarray(u_target, dtype=np.float64), **opts)
+        u = self.problem.u
+        eng.get_state(out=u._x)
+        u._touch()
+        self._pushed_version = ((id(u), u.version), None)
+        self._device_prev_is = u.version
+        return J, grad
+
+    def solve(self):
+        """One Newton-Krylov solve on the device; returns (iterations, converged) like DOLFIN."""
+        eng, opts, nl = self._prepare()
+        u = self.problem.u
         try:
             stats = eng.step(1, **opts)[0]
         except SolverNotConverged:

@@ -81,6 +81,39 @@ class TumorGrowth(FenicsSimulation):
         self.run(keep_nth=1, save_method=None, clear_all=False, plot=False, output_dir=output_dir)
         return self.solution
 
+    # -- inverse problem: value and gradient of the image misfit -------------------------------------
+    def _n_time_steps(self):
+        t, dt, n = 0.0, float(self.params.sim_time_step), 0
+        while t <= self.params.sim_time - 1e-5:          # the loop of `run` (simulation_base.py:285-312)
+            t += dt
+            n += 1
+        return n
+
+    def _set_controls(self, parameters):
+        self.params.diffusion, self.params.proliferation, self.params.coupling = parameters
+
+    def _controls_from_material_gradient(self, grad, labels):
+        """(dJ/d diffusion, dJ/d proliferation, dJ/d coupling): the three controls are uniform over the tissues."""
+        return np.asarray(grad).sum(axis=0)
+
+    def misfit_gradient(self, parameters, threshold_levels, threshold_targets, displacement_target=None):
+        """What the reference obtains from dolfin-adjoint for ``run_for_adjoint`` (image_based_optimization.py:660-767): the
+        misfit J = sum_l |th_l(c_N) - target_l|^2 + |u_N - u_target|^2 (mass-weighted L2, th_l the smooth threshold at level l,
+        :1404-1407) of the run with the given controls, and dJ/d(controls) -- one forward run and one backward sweep on the
+        device (``glims_adjoint``), time-independent coefficients.  Targets are scalar P1 functions (or vertex arrays), the
+        displacement target a vector P1 function (or [n_vertices, dim] array).  Returns (J, gradient)."""
+        self._set_controls(parameters)
+        u_previous = self.params.create_initial_value_function()
+        self._update_expressions(0.0)
+        self._setup_problem(u_previous)
+        arr = lambda f: np.asarray(f.vector().get_local() if hasattr(f, "vector") else f, dtype=np.float64)
+        nv = self.mesh.num_vertices()
+        targets = np.stack([arr(f).reshape(nv) for f in threshold_targets]) if len(threshold_levels) else np.zeros((0, nv))
+        ut = None if displacement_target is None else arr(displacement_target).reshape(nv, self.geometric_dimension)
+        J, grad = self.solver.adjoint_gradient(self._n_time_steps(), threshold_levels, targets, ut)
+        labels = np.unique(np.asarray(self.subdomains.subdomains.array()))
+        return J, self._controls_from_material_gradient(grad, labels)
+
     def init_postprocess(self, output_dir=config.output_dir_simulation_tmp):
         self.postprocess = PostProcessTumorGrowth(self.results, self.params, output_dir=output_dir,
                                                   engine=getattr(getattr(self, "solver", None), "_engine", None))

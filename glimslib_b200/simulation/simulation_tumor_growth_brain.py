@@ -62,6 +62,17 @@ class TumorGrowthBrain(TumorGrowth):
         self.run(keep_nth=1, save_method=None, clear_all=False, plot=False, output_dir=output_dir)
         return self.solution
 
+    def _set_controls(self, parameters):
+        p = self.params
+        p.D_WM, p.D_GM, p.rho_WM, p.rho_GM, p.coupling = parameters
+
+    def _controls_from_material_gradient(self, grad, labels):
+        """(dJ/dD_WM, dJ/dD_GM, dJ/drho_WM, dJ/drho_GM, dJ/dcoupling), the order of run_for_adjoint (brain:127-145)."""
+        grad = np.asarray(grad)
+        row = {self.subdomains.tissue_id_name_map.get(int(lab)): k for k, lab in enumerate(labels)}
+        pick = lambda name, col: float(grad[row[name], col]) if name in row else 0.0
+        return np.array([pick("WM", 0), pick("GM", 0), pick("WM", 1), pick("GM", 1), float(grad[:, 2].sum())])
+
     def init_postprocess(self, output_dir=config.output_dir_simulation_tmp):
         self.postprocess = PostProcessTumorGrowthBrain(self.results, self.params, output_dir=output_dir,
                                                        engine=getattr(getattr(self, "solver", None), "_engine", None))

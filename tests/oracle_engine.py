@@ -59,6 +59,23 @@ class OracleEngine:
         self.last_stats = stats
         return stats
 
+    def adjoint_gradient(self, n_steps, levels=(), level_targets=None, u_target=None, **opts):
+        """Same contract as Engine.adjoint_gradient, from oracle/adjoint.py with one control per (material, coefficient)."""
+        from oracle import adjoint
+        prob = self._prob()
+        n_mat = len(self.table)
+        spec = [(name, m) for m in range(n_mat) for name in ("D", "rho", "gamma")]
+        p = np.array([self.table[m][k] for m in range(n_mat) for k in (2, 3, 4)], dtype=float)
+        d = self.coords.shape[1]
+        targets = {"levels": {float(lv): np.asarray(level_targets)[i] for i, lv in enumerate(levels)}}
+        if u_target is not None:
+            targets["u"] = np.asarray(u_target, dtype=float).reshape(-1, d)
+        J, g = adjoint.gradient(prob, self.x_prev.copy(), int(n_steps), targets, p, spec)
+        xs = adjoint.forward(prob, self.x_prev.copy(), int(n_steps))
+        self.x, self.x_prev = xs[-1].copy(), xs[-1].copy()
+        self.calls.append("adjoint")
+        return float(J), np.asarray(g).reshape(n_mat, 3)
+
     def cell_fields(self, vertex=False):
         raise NotImplementedError("derived fields run on the device only")
 
