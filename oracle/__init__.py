@@ -23,7 +23,13 @@ golden vector for ``solver.solve()``.  What *is* pinned:
 * the closed-form P1 element tensors in :mod:`oracle.fem` are checked against a
   literal quadrature evaluation of the reference's weak-form text
   (:mod:`oracle.weakform`) and against finite differences;
+* closed-form solutions that P1 elements reproduce exactly -- free growth of a
+  minimally supported body (stress-free dilatation ``u = c*gamma*(x - x_fixed)``)
+  and the elasticity patch test -- are reproduced by the oracle to 1e-11
+  (``tests/test_oracle.py``) and, independently of the oracle, by the CUDA path
+  (``tests/test_gpu_analytic.py``);
 * the structural known answers of the reference's unit tests
   (``test_unit_subDomains.py:36-74``, ``test_unit_boundaryConditions.py:90-108``)
-  are reproduced in ``tests/test_oracle_reference_known_answers.py``.
+  are reproduced in ``tests/test_dropin_host.py``, and the reference's unit tests
+  themselves run unmodified in ``tests/test_reference_unit_tests_unmodified.py``.
 """

@@ -136,3 +136,23 @@ def test_amg_partition_study_reproduces_the_multi_gpu_iteration_penalty():
     assert its["local-drop"] > its["global"]
     assert its["local-keep"] <= its["global"] + 2
     assert its["local-keep"] < its["local-drop"]
+
+
+# ---- analytic known answers (tests/analytic_cases.py): the reference holds no number produced by solver.solve();
+# ---- these pin the discrete equations against closed-form solutions that P1 elements reproduce exactly ----------------------
+@pytest.mark.parametrize("d", [2, 3])
+def test_free_growth_is_a_stress_free_dilatation(d):
+    import analytic_cases as ac
+    prob, x0, exact, c = ac.free_growth_case(d)
+    _, x = solver.run(prob, x0, 1.0, linear="lu", rtol=1e-14, atol=1e-16)
+    X = x.reshape(-1, d + 1)
+    assert np.abs(X[:, d] - c).max() < 1e-13
+    assert np.abs(X[:, :d] - exact).max() < 1e-11 * np.abs(exact).max()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_elasticity_patch_test(d):
+    import analytic_cases as ac
+    prob, exact = ac.patch_case(d)
+    _, x = solver.run(prob, np.zeros(prob.ndof), 1.0, linear="lu", rtol=1e-14, atol=1e-16)
+    assert np.abs(x.reshape(-1, d + 1)[:, :d] - exact).max() < 1e-12 * np.abs(exact).max()
